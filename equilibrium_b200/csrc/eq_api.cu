@@ -1,0 +1,957 @@
+// eq_api.cu -- C ABI of libequilibrium_cuda.so (include/equilibrium_cuda.h):
+// handle, device memory, stream-ordered composition of Fluid::step
+// (fluid.rs:437-524) out of the kernels in k_*.cuh.
+#include "../../include/equilibrium_cuda.h"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <cmath>
+#include <new>
+#include <vector>
+
+#include "eq_common.cuh"
+#include "k_linsolve_exact.cuh"
+#include "k_linsolve_rb.cuh"
+#include "k_stencils.cuh"
+
+// ---------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int eq_fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(expr)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (expr);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return eq_fail(EQ_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_),    \
+                           __FILE__, __LINE__);                                                    \
+    } while (0)
+
+#define TRY(expr)                 \
+    do {                          \
+        int r_ = (expr);          \
+        if (r_ != EQ_OK) return r_; \
+    } while (0)
+
+#define NEED(h)                                                      \
+    do {                                                             \
+        if (!(h)) return eq_fail(EQ_ERR_INVALID, "null handle");     \
+        CU(cudaSetDevice((h)->dev));                                 \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// handle
+// ---------------------------------------------------------------------------
+enum { CAT_LS = 0, CAT_ADV, CAT_PROJ, CAT_BND, CAT_OTHER, CAT_COUNT };
+
+struct ProfSpan {
+    int cat;
+    cudaEvent_t a, b;
+};
+
+#define LSX_KMAX 256   // iterations per wavefront launch (bounds the job table and flag array)
+
+struct eq_fluid {
+    EqParams prm;
+    EqLayout L;
+    int dev;
+    int sm_count;
+    cudaStream_t own_stream, stream;
+    float *f[6];            // EQ_F_DENSITY .. EQ_F_SCRATCH
+    uint8_t *cells;
+    // mask-derived tables (rebuilt lazily when the mask changed)
+    uint8_t *codes, *row_fluid, *col_fluid;
+    unsigned *counts;       // [4] device
+    uint2 *row_list, *col_list;
+    unsigned n_row, n_col;
+    size_t cap_row, cap_col;
+    bool mask_dirty;
+    // exact wavefront workspace
+    float *raw[2];
+    unsigned *flags;        // [0] ticket, [1] error, [8..] progress
+    size_t flags_words;
+    std::map<int, uint32_t *> *job_tables;   // keyed by iterations-per-launch
+    int lsx_ctas;
+    // timing / profiling
+    cudaEvent_t ev0, ev1;
+    bool prof_on;
+    std::vector<ProfSpan> *spans;
+    std::vector<cudaEvent_t> *ev_pool;
+    double prof_ms[CAT_COUNT];
+    int64_t prof_launches[CAT_COUNT];
+    int64_t prof_cell_iters;
+    int64_t prof_steps;
+    void *l2buf;
+    size_t l2bytes;
+};
+
+static size_t field_elems(const eq_fluid *h) { return (size_t)h->L.P * h->L.rows; }
+
+struct ProfScope {
+    eq_fluid *h;
+    int cat;
+    bool timed;
+    cudaEvent_t a, b;
+    ProfScope(eq_fluid *h_, int cat_, int launches) : h(h_), cat(cat_), timed(false) {
+        h->prof_launches[cat] += launches;
+        if (h->prof_on) {
+            auto get = [&]() {
+                cudaEvent_t e;
+                if (!h->ev_pool->empty()) {
+                    e = h->ev_pool->back();
+                    h->ev_pool->pop_back();
+                } else {
+                    cudaEventCreate(&e);
+                }
+                return e;
+            };
+            a = get();
+            b = get();
+            cudaEventRecord(a, h->stream);
+            timed = true;
+        }
+    }
+    ~ProfScope() {
+        if (timed) {
+            cudaEventRecord(b, h->stream);
+            h->spans->push_back(ProfSpan{cat, a, b});
+        }
+    }
+};
+
+static int prof_collect(eq_fluid *h) {
+    if (h->spans->empty()) return EQ_OK;
+    CU(cudaStreamSynchronize(h->stream));
+    for (auto &s : *h->spans) {
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, s.a, s.b));
+        h->prof_ms[s.cat] += ms;
+        h->ev_pool->push_back(s.a);
+        h->ev_pool->push_back(s.b);
+    }
+    h->spans->clear();
+    return EQ_OK;
+}
+
+static inline dim3 row_grid(const eq_fluid *h, int rows, int threads = 256) {
+    return dim3((unsigned)((h->L.N + threads - 1) / threads), (unsigned)rows, 1);
+}
+
+static int check_launch(const char *what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return eq_fail(EQ_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+    return EQ_OK;
+}
+
+// ---------------------------------------------------------------------------
+// mask tables
+// ---------------------------------------------------------------------------
+static int ensure_tables(eq_fluid *h) {
+    if (!h->mask_dirty) return EQ_OK;
+    ProfScope ps(h, CAT_OTHER, 2);
+    const EqLayout L = h->L;
+    CU(cudaMemsetAsync(h->counts, 0, 4 * sizeof(unsigned), h->stream));
+    CU(cudaMemsetAsync(h->row_fluid, 0, L.N, h->stream));
+    CU(cudaMemsetAsync(h->col_fluid, 0, L.N, h->stream));
+    EQ_LAUNCH(k_build_codes, row_grid(h, L.N), 256, 0, h->stream, h->cells, h->codes, h->row_fluid, h->col_fluid,
+                                                           h->counts, nullptr, nullptr, 0, L);
+    TRY(check_launch("k_build_codes"));
+    unsigned counts[4];
+    CU(cudaMemcpyAsync(counts, h->counts, sizeof(counts), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (counts[0] > h->cap_row) {
+        if (h->row_list) CU(cudaFree(h->row_list));
+        h->row_list = nullptr;
+        h->cap_row = (size_t)counts[0] + counts[0] / 4 + 1024;
+        CU(cudaMalloc(&h->row_list, h->cap_row * sizeof(uint2)));
+    }
+    if (counts[1] > h->cap_col) {
+        if (h->col_list) CU(cudaFree(h->col_list));
+        h->col_list = nullptr;
+        h->cap_col = (size_t)counts[1] + counts[1] / 4 + 1024;
+        CU(cudaMalloc(&h->col_list, h->cap_col * sizeof(uint2)));
+    }
+    EQ_LAUNCH(k_build_codes, row_grid(h, L.N), 256, 0, h->stream, h->cells, h->codes, h->row_fluid, h->col_fluid,
+                                                           h->counts, h->row_list, h->col_list, 1, L);
+    TRY(check_launch("k_build_codes(lists)"));
+    h->n_row = counts[0];
+    h->n_col = counts[1];
+    h->mask_dirty = false;
+    return EQ_OK;
+}
+
+// ---------------------------------------------------------------------------
+// set_boundaries (fluid.rs:252-272) as a sparse pass
+// ---------------------------------------------------------------------------
+static int set_boundaries(eq_fluid *h, int orient, float *x) {
+    TRY(ensure_tables(h));
+    ProfScope ps(h, CAT_BND, 1);
+    const EqLayout L = h->L;
+    if (orient == EQ_PASSIVE) {
+        const int threads = 256, blocks = (L.N + threads - 1) / threads;
+        EQ_LAUNCH(k_bnd_passive, blocks, threads, 0, h->stream, x, h->row_fluid, h->col_fluid, L);
+        return check_launch("k_bnd_passive");
+    }
+    const uint2 *list = orient == EQ_ADJUST_ROW ? h->row_list : h->col_list;
+    const unsigned n = orient == EQ_ADJUST_ROW ? h->n_row : h->n_col;
+    const int threads = 256;
+    const unsigned blocks = std::max(1u, (n + threads - 1) / threads);
+    EQ_LAUNCH(k_bnd_list, blocks, threads, 0, h->stream, x, list, n, L);
+    return check_launch("k_bnd_list");
+}
+
+// ---------------------------------------------------------------------------
+// lin_solve (fluid.rs:301-325)
+// ---------------------------------------------------------------------------
+struct LinSolveReq {
+    int orient;
+    float *x;
+    const float *x0;
+    float a, c;
+};
+
+static int get_job_table(eq_fluid *h, int kc, const uint32_t **out) {
+    auto it = h->job_tables->find(kc);
+    if (it != h->job_tables->end()) {
+        *out = it->second;
+        return EQ_OK;
+    }
+    const int NB = (h->L.N - 2 + 31) / 32;
+    std::vector<uint32_t> tab;
+    tab.reserve((size_t)kc * NB);
+    // wavefront order: w = b + 2k ascending; a job depends only on w-1
+    for (int w = 0; w <= (NB - 1) + 2 * (kc - 1); ++w)
+        for (int k = 0; k < kc; ++k) {
+            const int b = w - 2 * k;
+            if (b >= 0 && b < NB) tab.push_back(((uint32_t)k << 16) | (uint32_t)b);
+        }
+    uint32_t *d = nullptr;
+    CU(cudaMalloc(&d, tab.size() * sizeof(uint32_t)));
+    CU(cudaMemcpyAsync(d, tab.data(), tab.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));   // `tab` is pageable and goes out of scope
+    (*h->job_tables)[kc] = d;
+    *out = d;
+    return EQ_OK;
+}
+
+static int lin_solve_exact(eq_fluid *h, const LinSolveReq *req, int nreq, int64_t iters) {
+    const EqLayout L = h->L;
+    const int NB = (L.N - 2 + 31) / 32;
+    const int NC = (L.N + 31) / 32;
+    int64_t done = 0;
+    while (done < iters) {
+        const int kc = (int)std::min<int64_t>(LSX_KMAX, iters - done);
+        const uint32_t *jobs = nullptr;
+        TRY(get_job_table(h, kc, &jobs));
+        LsxParams p;
+        memset(&p, 0, sizeof(p));
+        p.nprob = nreq;
+        const size_t prog_words = (size_t)kc * NB;
+        for (int i = 0; i < nreq; ++i) {
+            p.prob[i].x = req[i].x;
+            p.prob[i].x0 = req[i].x0;
+            p.prob[i].raw = h->raw[i];
+            p.prob[i].progress = h->flags + 8 + (size_t)i * prog_words;
+            p.prob[i].a = req[i].a;
+            p.prob[i].c_recip = 1.0f / req[i].c;                       // fluid.rs:311
+            p.prob[i].orient = req[i].orient;
+        }
+        p.codes = h->codes;
+        p.row_fluid = h->row_fluid;
+        p.col_fluid = h->col_fluid;
+        p.jobs = jobs;
+        p.njobs = kc * NB;
+        p.N = L.N;
+        p.P = L.P;
+        p.K = kc;
+        p.NB = NB;
+        p.NC = NC;
+        p.ticket = h->flags;
+        p.error = reinterpret_cast<int *>(h->flags + 1);
+        // ticket := 0, progress := 0; the sticky error word is left alone
+        CU(cudaMemsetAsync(h->flags, 0, sizeof(unsigned), h->stream));
+        CU(cudaMemsetAsync(h->flags + 8, 0, (size_t)nreq * prog_words * sizeof(unsigned), h->stream));
+        const int grid = std::min(h->lsx_ctas, p.njobs * nreq);
+        EQ_LAUNCH(k_linsolve_exact, grid, 32, sizeof(LsxSmem), h->stream, p);
+        TRY(check_launch("k_linsolve_exact"));
+        done += kc;
+    }
+    for (int i = 0; i < nreq; ++i) {
+        EQ_LAUNCH(k_corners, 1, 32, 0, h->stream, req[i].x, L);
+        TRY(check_launch("k_corners"));
+    }
+    return EQ_OK;
+}
+
+static int lin_solve_red_black(eq_fluid *h, const LinSolveReq *req, int nreq, int64_t iters) {
+    const EqLayout L = h->L;
+    const int threads = 256;
+    const dim3 grid((unsigned)((L.N / 2 + threads) / threads), (unsigned)(L.N - 2), 1);
+    for (int64_t k = 0; k < iters; ++k) {
+        for (int i = 0; i < nreq; ++i) {
+            const float c_recip = 1.0f / req[i].c;
+            EQ_LAUNCH(k_rb_half, grid, threads, 0, h->stream, req[i].x, req[i].x0, req[i].a, c_recip, 0, L);
+            EQ_LAUNCH(k_rb_half, grid, threads, 0, h->stream, req[i].x, req[i].x0, req[i].a, c_recip, 1, L);
+            TRY(check_launch("k_rb_half"));
+            // fused into the same category: the boundary pass is part of the iteration
+            if (req[i].orient == EQ_PASSIVE) {
+                EQ_LAUNCH(k_bnd_passive, (L.N + 255) / 256, 256, 0, h->stream, req[i].x, h->row_fluid, h->col_fluid, L);
+            } else {
+                const uint2 *list = req[i].orient == EQ_ADJUST_ROW ? h->row_list : h->col_list;
+                const unsigned n = req[i].orient == EQ_ADJUST_ROW ? h->n_row : h->n_col;
+                EQ_LAUNCH(k_bnd_list, std::max(1u, (n + 255u) / 256u), 256, 0, h->stream, req[i].x, list, n, L);
+            }
+            TRY(check_launch("boundary in red-black"));
+        }
+    }
+    return EQ_OK;
+}
+
+static int lin_solve(eq_fluid *h, const LinSolveReq *req, int nreq, int64_t iters) {
+    if (iters <= 0) return EQ_OK;   // `for _k in 0..frames` runs zero times
+    TRY(ensure_tables(h));
+    const int64_t cells = (int64_t)(h->L.N - 2) * (h->L.N - 2);
+    h->prof_cell_iters += cells * iters * nreq;
+    if (h->prm.mode == EQ_MODE_RED_BLACK) {
+        ProfScope ps(h, CAT_LS, (int)(3 * iters * nreq));
+        return lin_solve_red_black(h, req, nreq, iters);
+    }
+    ProfScope ps(h, CAT_LS, (int)((iters + LSX_KMAX - 1) / LSX_KMAX) + nreq);
+    return lin_solve_exact(h, req, nreq, iters);
+}
+
+// diffuse (fluid.rs:276-298): a = dt * diff * (N-2) * (N-2), c = 1 + 4a
+static LinSolveReq diffuse_req(const eq_fluid *h, int orient, float *x, const float *x0, float diff) {
+    const float sf = (float)(h->L.N - 2);
+    float a = h->prm.delta_t * diff;
+    a = a * sf;
+    a = a * sf;
+    return LinSolveReq{orient, x, x0, a, 1.0f + 4.0f * a};
+}
+
+// project (fluid.rs:330-375)
+static int project(eq_fluid *h, float *vx, float *vy, float *p, float *div, int64_t iters) {
+    const EqLayout L = h->L;
+    {
+        ProfScope ps(h, CAT_PROJ, 1);
+        EQ_LAUNCH(k_divergence, row_grid(h, L.N - 2), 256, 0, h->stream, vx, vy, div, p, L);
+        TRY(check_launch("k_divergence"));
+    }
+    TRY(set_boundaries(h, EQ_PASSIVE, div));                           // :351
+    TRY(set_boundaries(h, EQ_PASSIVE, p));                             // :352
+    LinSolveReq r{EQ_PASSIVE, p, div, 1.0f, 4.0f};
+    TRY(lin_solve(h, &r, 1, iters));                                   // :353-362
+    {
+        ProfScope ps(h, CAT_PROJ, 1);
+        EQ_LAUNCH(k_gradient, row_grid(h, L.N - 2), 256, 0, h->stream, vx, vy, p, L);
+        TRY(check_launch("k_gradient"));
+    }
+    TRY(set_boundaries(h, EQ_ADJUST_ROW, vx));                         // :373
+    TRY(set_boundaries(h, EQ_ADJUST_COLUMN, vy));                      // :374
+    return EQ_OK;
+}
+
+// advect (fluid.rs:378-432) for one field, or for the velocity pair that shares its back-trace
+static int advect(eq_fluid *h, int orientA, float *dA, const float *d0A, int orientB, float *dB,
+                  const float *d0B, const float *vx, const float *vy) {
+    const EqLayout L = h->L;
+    {
+        ProfScope ps(h, CAT_ADV, 1);
+        if (dB)
+            EQ_LAUNCH((k_advect<2>), L.N - 2, 256, 0, h->stream, dA, d0A, dB, d0B, vx, vy, h->prm.delta_t, L);
+        else
+            EQ_LAUNCH((k_advect<1>), L.N - 2, 256, 0, h->stream, dA, d0A, nullptr, nullptr, vx, vy, h->prm.delta_t, L);
+        TRY(check_launch("k_advect"));
+    }
+    TRY(set_boundaries(h, orientA, dA));                               // :431
+    if (dB) TRY(set_boundaries(h, orientB, dB));
+    return EQ_OK;
+}
+
+static int64_t gs_iters(const eq_fluid *h) {
+    return h->prm.gs_iterations ? h->prm.gs_iterations : h->prm.frames;   // fluid.rs:445 (quirk Q1)
+}
+
+// Fluid::step (fluid.rs:437-524)
+static int step_once(eq_fluid *h) {
+    float *density = h->f[EQ_F_DENSITY], *vx = h->f[EQ_F_VX], *vy = h->f[EQ_F_VY];
+    float *vx0 = h->f[EQ_F_VX0], *vy0 = h->f[EQ_F_VY0], *scratch = h->f[EQ_F_SCRATCH];
+    const int64_t k = gs_iters(h);
+    // :438-457  the two velocity diffusions are independent: one wavefront launch
+    LinSolveReq d2[2] = {diffuse_req(h, EQ_ADJUST_ROW, vx0, vx, h->prm.viscosity),
+                         diffuse_req(h, EQ_ADJUST_COLUMN, vy0, vy, h->prm.viscosity)};
+    TRY(lin_solve(h, d2, 2, k));
+    TRY(project(h, vx0, vy0, vx, vy, k));                              // :459-467
+    TRY(advect(h, EQ_ADJUST_ROW, vx, vx0, EQ_ADJUST_COLUMN, vy, vy0, vx0, vy0));   // :469-489
+    TRY(project(h, vx, vy, vx0, vy0, k));                              // :491-499
+    LinSolveReq dd = diffuse_req(h, EQ_PASSIVE, scratch, density, h->prm.diffusion);
+    TRY(lin_solve(h, &dd, 1, k));                                      // :501-510
+    TRY(advect(h, EQ_PASSIVE, density, scratch, 0, nullptr, nullptr, vx, vy));     // :512-521
+    {
+        ProfScope ps(h, CAT_OTHER, 1);
+        CU(cudaMemcpyAsync(scratch, density, field_elems(h) * sizeof(float), cudaMemcpyDeviceToDevice,
+                           h->stream));                                // :523
+    }
+    h->prof_steps += 1;
+    return EQ_OK;
+}
+
+// ---------------------------------------------------------------------------
+// construction
+// ---------------------------------------------------------------------------
+static int validate_params(const EqParams *p) {
+    if (!p) return eq_fail(EQ_ERR_INVALID, "null params");
+    if (p->size < 20 || p->size > 32768)
+        return eq_fail(EQ_ERR_INVALID, "size %u out of range [20, 32768] (init_density underflows below 20, fluid.rs:534)",
+                       p->size);
+    if (p->frames < 0 || p->gs_iterations < 0) return eq_fail(EQ_ERR_INVALID, "negative frames / gs_iterations");
+    if (p->mode != EQ_MODE_EXACT && p->mode != EQ_MODE_RED_BLACK) return eq_fail(EQ_ERR_INVALID, "unknown mode %d", p->mode);
+    if (p->world > 1) return eq_fail(EQ_ERR_INVALID, "multi-GPU slabs are not implemented in this build");
+    return EQ_OK;
+}
+
+static int alloc_handle(const EqParams *params, eq_fluid **out) {
+    TRY(validate_params(params));
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (ndev <= 0) return eq_fail(EQ_ERR_CUDA, "no CUDA device (there is no CPU fallback)");
+    if (params->device < 0 || params->device >= ndev) return eq_fail(EQ_ERR_INVALID, "device %d not in [0,%d)", params->device, ndev);
+    CU(cudaSetDevice(params->device));
+    eq_fluid *h = new (std::nothrow) eq_fluid();
+    if (!h) return eq_fail(EQ_ERR_NOMEM, "host allocation failed");
+    memset(h->f, 0, sizeof(h->f));
+    h->prm = *params;
+    h->dev = params->device;
+    h->L.N = (int)params->size;
+    h->L.P = ((int)params->size + 31) / 32 * 32;
+    h->L.rows = (int)params->size + EQ_ROW_PAD;
+    h->spans = new std::vector<ProfSpan>();
+    h->ev_pool = new std::vector<cudaEvent_t>();
+    h->job_tables = new std::map<int, uint32_t *>();
+    h->mask_dirty = true;
+    *out = h;   // so that the caller can destroy a half-built handle
+    CU(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->dev));
+    CU(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    h->stream = h->own_stream;
+    CU(cudaEventCreate(&h->ev0));
+    CU(cudaEventCreate(&h->ev1));
+    const size_t elems = field_elems(h);
+    for (int i = 0; i < 6; ++i) {
+        CU(cudaMalloc(&h->f[i], elems * sizeof(float)));
+        CU(cudaMemsetAsync(h->f[i], 0, elems * sizeof(float), h->stream));
+    }
+    CU(cudaMalloc(&h->cells, elems));
+    CU(cudaMemsetAsync(h->cells, 0, elems, h->stream));
+    CU(cudaMalloc(&h->codes, elems));
+    CU(cudaMemsetAsync(h->codes, 0, elems, h->stream));
+    CU(cudaMalloc(&h->row_fluid, h->L.N));
+    CU(cudaMalloc(&h->col_fluid, h->L.N));
+    CU(cudaMalloc(&h->counts, 4 * sizeof(unsigned)));
+    const int NB = (h->L.N - 2 + 31) / 32;
+    for (int i = 0; i < 2; ++i) {
+        CU(cudaMalloc(&h->raw[i], (size_t)NB * h->L.P * sizeof(float)));
+        CU(cudaMemsetAsync(h->raw[i], 0, (size_t)NB * h->L.P * sizeof(float), h->stream));
+    }
+    h->flags_words = 8 + 2 * (size_t)LSX_KMAX * NB;
+    CU(cudaMalloc(&h->flags, h->flags_words * sizeof(unsigned)));
+    CU(cudaMemsetAsync(h->flags, 0, h->flags_words * sizeof(unsigned), h->stream));
+    CU(cudaFuncSetAttribute(k_linsolve_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LsxSmem)));
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_linsolve_exact, 32, sizeof(LsxSmem)));
+    h->lsx_ctas = std::max(1, per_sm) * h->sm_count;
+    return EQ_OK;
+}
+
+static int clamp_i64(int64_t v, int64_t lo, int64_t hi) { return (int)(v < lo ? lo : (v > hi ? hi : v)); }
+
+static int launch_add_rect(eq_fluid *h, float *f, int x0, int y0, int x1, int y1, float amount) {
+    if (x1 <= x0 || y1 <= y0) return EQ_OK;
+    dim3 grid((unsigned)((x1 - x0 + 255) / 256), (unsigned)(y1 - y0), 1);
+    EQ_LAUNCH(k_add_rect, grid, 256, 0, h->stream, f, x0, y0, x1, y1, amount, h->L);
+    return check_launch("k_add_rect");
+}
+
+static int launch_cells_rect(eq_fluid *h, int x0, int y0, int x1, int y1, uint8_t v) {
+    if (x1 <= x0 || y1 <= y0) return EQ_OK;
+    dim3 grid((unsigned)((x1 - x0 + 255) / 256), (unsigned)(y1 - y0), 1);
+    EQ_LAUNCH(k_set_cells_rect, grid, 256, 0, h->stream, h->cells, x0, y0, x1, y1, v, h->L);
+    h->mask_dirty = true;
+    return check_launch("k_set_cells_rect");
+}
+
+static int init_walls(eq_fluid *h) {   // fluid.rs:552-570
+    const int N = h->L.N;
+    TRY(launch_cells_rect(h, 0, 0, N, 1, 1));
+    TRY(launch_cells_rect(h, 0, N - 1, N, N, 1));
+    TRY(launch_cells_rect(h, 0, 0, 1, N, 1));
+    TRY(launch_cells_rect(h, N - 1, 0, N, N, 1));
+    return EQ_OK;
+}
+
+static int init_default(eq_fluid *h) {   // fluid.rs:602-606
+    const int N = h->L.N, c = N / 2;
+    ProfScope ps(h, CAT_OTHER, 8);
+    TRY(launch_add_rect(h, h->f[EQ_F_VX], 0, 0, N, N, 1.0f));                       // :542-548
+    TRY(launch_add_rect(h, h->f[EQ_F_VY], 0, 0, N, N, 1.0f));
+    TRY(launch_add_rect(h, h->f[EQ_F_DENSITY], c - 10, c - 10, c + 11, c + 11, 0.9f));   // :534-538
+    TRY(launch_add_rect(h, h->f[EQ_F_SCRATCH], c - 10, c - 10, c + 11, c + 11, 0.9f));
+    return init_walls(h);
+}
+
+// ---------------------------------------------------------------------------
+// exported API
+// ---------------------------------------------------------------------------
+extern "C" {
+
+const char *eq_last_error(void) { return g_err; }
+int eq_abi_version(void) { return EQ_ABI_VERSION; }
+
+int eq_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int eq_destroy(eq_fluid *h) {
+    if (!h) return EQ_OK;
+    cudaSetDevice(h->dev);
+    if (h->own_stream) cudaStreamSynchronize(h->own_stream);
+    for (int i = 0; i < 6; ++i) cudaFree(h->f[i]);
+    cudaFree(h->cells);
+    cudaFree(h->codes);
+    cudaFree(h->row_fluid);
+    cudaFree(h->col_fluid);
+    cudaFree(h->counts);
+    cudaFree(h->row_list);
+    cudaFree(h->col_list);
+    cudaFree(h->raw[0]);
+    cudaFree(h->raw[1]);
+    cudaFree(h->flags);
+    cudaFree(h->l2buf);
+    if (h->job_tables) {
+        for (auto &kv : *h->job_tables) cudaFree(kv.second);
+        delete h->job_tables;
+    }
+    if (h->spans) {
+        for (auto &s : *h->spans) {
+            cudaEventDestroy(s.a);
+            cudaEventDestroy(s.b);
+        }
+        delete h->spans;
+    }
+    if (h->ev_pool) {
+        for (auto e : *h->ev_pool) cudaEventDestroy(e);
+        delete h->ev_pool;
+    }
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+    return EQ_OK;
+}
+
+int eq_create(const EqParams *params, eq_fluid **out) {
+    if (!out) return eq_fail(EQ_ERR_INVALID, "null out pointer");
+    *out = nullptr;
+    int r = alloc_handle(params, out);
+    if (r == EQ_OK) r = init_default(*out);                            // Fluid::new calls init(), fluid.rs:108
+    if (r != EQ_OK) {
+        eq_destroy(*out);
+        *out = nullptr;
+    }
+    return r;
+}
+
+int eq_clone(eq_fluid *h, eq_fluid **out) {
+    NEED(h);
+    if (!out) return eq_fail(EQ_ERR_INVALID, "null out pointer");
+    *out = nullptr;
+    int r = alloc_handle(&h->prm, out);
+    if (r != EQ_OK) {
+        eq_destroy(*out);
+        *out = nullptr;
+        return r;
+    }
+    eq_fluid *c = *out;
+    const size_t elems = field_elems(h);
+    CU(cudaStreamSynchronize(c->stream));   // the clone's memsets ran on its own stream
+    for (int i = 0; i < 6; ++i)
+        CU(cudaMemcpyAsync(c->f[i], h->f[i], elems * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+    CU(cudaMemcpyAsync(c->cells, h->cells, elems, cudaMemcpyDeviceToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    c->mask_dirty = true;
+    return EQ_OK;
+}
+
+int eq_init_default(eq_fluid *h) {
+    NEED(h);
+    return init_default(h);
+}
+
+int eq_add_density(eq_fluid *h, uint32_t x, uint32_t y, float amount) {
+    NEED(h);
+    const int N = h->L.N;
+    const unsigned o = (unsigned)std::min<uint32_t>(x, N - 1) + (unsigned)std::min<uint32_t>(y, N - 1) * (unsigned)h->L.P;
+    ProfScope ps(h, CAT_OTHER, 1);
+    EQ_LAUNCH(k_add_source, 1, 32, 0, h->stream, h->f[EQ_F_DENSITY], h->f[EQ_F_SCRATCH], h->f[EQ_F_VX], h->f[EQ_F_VY], o,
+                                          amount, 0.f, 0.f, 1);
+    return check_launch("k_add_source");
+}
+
+int eq_add_velocity(eq_fluid *h, uint32_t x, uint32_t y, float ax, float ay) {
+    NEED(h);
+    const int N = h->L.N;
+    const unsigned o = (unsigned)std::min<uint32_t>(x, N - 1) + (unsigned)std::min<uint32_t>(y, N - 1) * (unsigned)h->L.P;
+    ProfScope ps(h, CAT_OTHER, 1);
+    EQ_LAUNCH(k_add_source, 1, 32, 0, h->stream, h->f[EQ_F_DENSITY], h->f[EQ_F_SCRATCH], h->f[EQ_F_VX], h->f[EQ_F_VY], o,
+                                          0.f, ax, ay, 2);
+    return check_launch("k_add_source");
+}
+
+int eq_rect_valid(int64_t x0, int64_t y0, int64_t x1, int64_t y1, int64_t size) {
+    return x0 != x1 && y0 != y1 && x0 < x1 && y0 < y1 && x0 < size && y0 < size && x1 < size && y1 < size;
+}
+
+int eq_fill_rect(eq_fluid *h, int64_t x0, int64_t y0, int64_t x1, int64_t y1) {
+    NEED(h);
+    if (x0 >= x1 || y0 >= y1) return EQ_OK;                            // empty Rust ranges
+    const int N = h->L.N;
+    // {clamp(x) : x in [x0,x1)} is the contiguous range [clamp(x0), clamp(x1-1)]
+    const int cx0 = clamp_i64(x0, 0, N - 1), cx1 = clamp_i64(x1 - 1, 0, N - 1) + 1;
+    const int cy0 = clamp_i64(y0, 0, N - 1), cy1 = clamp_i64(y1 - 1, 0, N - 1) + 1;
+    ProfScope ps(h, CAT_OTHER, 1);
+    return launch_cells_rect(h, cx0, cy0, cx1, cy1, 1);
+}
+
+int eq_reset_walls(eq_fluid *h) {
+    NEED(h);
+    ProfScope ps(h, CAT_OTHER, 5);
+    TRY(launch_cells_rect(h, 0, 0, h->L.N, h->L.N, 0));
+    return init_walls(h);
+}
+
+int eq_set_params(eq_fluid *h, const EqParams *p) {
+    NEED(h);
+    if (!p) return eq_fail(EQ_ERR_INVALID, "null params");
+    if (p->size != h->prm.size) return eq_fail(EQ_ERR_INVALID, "size is fixed at creation (the reference builds a new Fluid, renderer.rs:145-149)");
+    if (p->frames < 0 || p->gs_iterations < 0) return eq_fail(EQ_ERR_INVALID, "negative frames / gs_iterations");
+    if (p->mode != EQ_MODE_EXACT && p->mode != EQ_MODE_RED_BLACK) return eq_fail(EQ_ERR_INVALID, "unknown mode %d", p->mode);
+    h->prm.delta_t = p->delta_t;
+    h->prm.frames = p->frames;
+    h->prm.gs_iterations = p->gs_iterations;
+    h->prm.diffusion = p->diffusion;
+    h->prm.viscosity = p->viscosity;
+    h->prm.mode = p->mode;
+    return EQ_OK;
+}
+
+int eq_get_params(eq_fluid *h, EqParams *out) {
+    if (!h || !out) return eq_fail(EQ_ERR_INVALID, "null argument");
+    *out = h->prm;
+    return EQ_OK;
+}
+
+int eq_step(eq_fluid *h) {
+    NEED(h);
+    return step_once(h);
+}
+
+int eq_step_n(eq_fluid *h, int64_t n, const EqSource *sources, int64_t n_sources) {
+    NEED(h);
+    if (n < 0 || n_sources < 0 || (n_sources > 0 && !sources)) return eq_fail(EQ_ERR_INVALID, "bad step_n arguments");
+    int64_t s = 0;
+    for (int64_t fr = 0; fr < n; ++fr) {
+        while (s < n_sources && sources[s].frame <= fr) {
+            if (sources[s].frame == fr) {
+                const int N = h->L.N;
+                const unsigned o = (unsigned)std::min<uint32_t>(sources[s].x, N - 1) +
+                                   (unsigned)std::min<uint32_t>(sources[s].y, N - 1) * (unsigned)h->L.P;
+                const int what = (sources[s].d_density != 0.f ? 1 : 0) | 2;
+                ProfScope ps(h, CAT_OTHER, 1);
+                EQ_LAUNCH(k_add_source, 1, 32, 0, h->stream, h->f[EQ_F_DENSITY], h->f[EQ_F_SCRATCH], h->f[EQ_F_VX],
+                                                      h->f[EQ_F_VY], o, sources[s].d_density, sources[s].d_vx,
+                                                      sources[s].d_vy, what);
+                TRY(check_launch("k_add_source"));
+            }
+            ++s;
+        }
+        TRY(step_once(h));
+    }
+    return EQ_OK;
+}
+
+static int check_device_error(eq_fluid *h) {
+    int err = 0;
+    CU(cudaMemcpyAsync(&err, h->flags + 1, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (err != 0) return eq_fail(EQ_ERR_TIMEOUT, "wavefront watchdog fired (code %d): a lin_solve job waited too long", err);
+    return EQ_OK;
+}
+
+int eq_sync(eq_fluid *h) {
+    NEED(h);
+    CU(cudaStreamSynchronize(h->stream));
+    return check_device_error(h);
+}
+
+static int field_ptr(eq_fluid *h, int field, void **ptr, size_t *esize) {
+    if (field >= 0 && field < 6) {
+        *ptr = h->f[field];
+        *esize = sizeof(float);
+        return EQ_OK;
+    }
+    if (field == EQ_F_CELLS) {
+        *ptr = h->cells;
+        *esize = 1;
+        return EQ_OK;
+    }
+    return eq_fail(EQ_ERR_INVALID, "unknown field id %d", field);
+}
+
+int eq_upload_rows(eq_fluid *h, int field, uint32_t row_begin, uint32_t n_rows, const void *host) {
+    NEED(h);
+    void *d;
+    size_t es;
+    TRY(field_ptr(h, field, &d, &es));
+    const uint32_t N = (uint32_t)h->L.N;
+    if (!host || row_begin > N || n_rows > N - row_begin) return eq_fail(EQ_ERR_INVALID, "bad row range");
+    if (n_rows == 0) return EQ_OK;
+    if (field == EQ_F_CELLS) {
+        const uint8_t *c = static_cast<const uint8_t *>(host);
+        for (uint32_t r = 0; r < n_rows; ++r) {
+            const uint32_t j = row_begin + r;
+            const uint8_t *row = c + (size_t)r * N;
+            for (uint32_t i = 0; i < N; ++i)
+                if (row[i] > 1) return eq_fail(EQ_ERR_INVALID, "cells_type must be 0 (NoWall) or 1 (DefaultWall)");
+            const bool frame_row = (j == 0 || j == N - 1);
+            if (frame_row) {
+                for (uint32_t i = 0; i < N; ++i)
+                    if (!row[i]) return eq_fail(EQ_ERR_INVALID, "frame cell (%u,%u) must be DefaultWall (init_walls, fluid.rs:552-570)", i, j);
+            } else if (!row[0] || !row[N - 1]) {
+                return eq_fail(EQ_ERR_INVALID, "frame cells of row %u must be DefaultWall (init_walls, fluid.rs:552-570)", j);
+            }
+        }
+        h->mask_dirty = true;
+    }
+    ProfScope ps(h, CAT_OTHER, 0);
+    CU(cudaMemcpy2DAsync(static_cast<char *>(d) + (size_t)row_begin * h->L.P * es, (size_t)h->L.P * es, host,
+                         (size_t)N * es, (size_t)N * es, n_rows, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));   // the host buffer is only borrowed for the call
+    return EQ_OK;
+}
+
+int eq_download_rows(eq_fluid *h, int field, uint32_t row_begin, uint32_t n_rows, void *host) {
+    NEED(h);
+    void *d;
+    size_t es;
+    TRY(field_ptr(h, field, &d, &es));
+    const uint32_t N = (uint32_t)h->L.N;
+    if (!host || row_begin > N || n_rows > N - row_begin) return eq_fail(EQ_ERR_INVALID, "bad row range");
+    if (n_rows > 0) {
+        ProfScope ps(h, CAT_OTHER, 0);
+        CU(cudaMemcpy2DAsync(host, (size_t)N * es, static_cast<char *>(d) + (size_t)row_begin * h->L.P * es,
+                             (size_t)h->L.P * es, (size_t)N * es, n_rows, cudaMemcpyDeviceToHost, h->stream));
+    }
+    return check_device_error(h);   // synchronises the stream
+}
+
+int eq_upload(eq_fluid *h, int field, const void *host, size_t bytes) {
+    NEED(h);
+    const size_t es = field == EQ_F_CELLS ? 1 : sizeof(float);
+    if (bytes != (size_t)h->L.N * h->L.N * es) return eq_fail(EQ_ERR_INVALID, "eq_upload: expected %zu bytes, got %zu", (size_t)h->L.N * h->L.N * es, bytes);
+    return eq_upload_rows(h, field, 0, (uint32_t)h->L.N, host);
+}
+
+int eq_download(eq_fluid *h, int field, void *host, size_t bytes) {
+    NEED(h);
+    const size_t es = field == EQ_F_CELLS ? 1 : sizeof(float);
+    if (bytes != (size_t)h->L.N * h->L.N * es) return eq_fail(EQ_ERR_INVALID, "eq_download: expected %zu bytes, got %zu", (size_t)h->L.N * h->L.N * es, bytes);
+    return eq_download_rows(h, field, 0, (uint32_t)h->L.N, host);
+}
+
+int eq_owned_rows(eq_fluid *h, uint32_t *row_begin, uint32_t *row_end) {
+    if (!h || !row_begin || !row_end) return eq_fail(EQ_ERR_INVALID, "null argument");
+    *row_begin = 0;
+    *row_end = (uint32_t)h->L.N;
+    return EQ_OK;
+}
+
+static int f32_field(eq_fluid *h, int id, float **out) {
+    if (id < 0 || id >= 6) return eq_fail(EQ_ERR_INVALID, "field id %d is not an f32 field", id);
+    *out = h->f[id];
+    return EQ_OK;
+}
+
+static bool valid_orient(int o) { return o == EQ_ADJUST_ROW || o == EQ_ADJUST_COLUMN || o == EQ_PASSIVE; }
+
+int eq_op_set_boundaries(eq_fluid *h, int orientation, int field) {
+    NEED(h);
+    float *x;
+    TRY(f32_field(h, field, &x));
+    if (!valid_orient(orientation)) return eq_fail(EQ_ERR_INVALID, "bad orientation");
+    return set_boundaries(h, orientation, x);
+}
+
+int eq_op_lin_solve(eq_fluid *h, int orientation, int x_field, int x0_field, float a, float c, int64_t iters) {
+    NEED(h);
+    float *x, *x0;
+    TRY(f32_field(h, x_field, &x));
+    TRY(f32_field(h, x0_field, &x0));
+    if (!valid_orient(orientation) || x == x0 || iters < 0) return eq_fail(EQ_ERR_INVALID, "bad lin_solve arguments");
+    LinSolveReq r{orientation, x, x0, a, c};
+    return lin_solve(h, &r, 1, iters);
+}
+
+int eq_op_diffuse(eq_fluid *h, int orientation, int x_field, int x0_field, float diffusion, int64_t iters) {
+    NEED(h);
+    float *x, *x0;
+    TRY(f32_field(h, x_field, &x));
+    TRY(f32_field(h, x0_field, &x0));
+    if (!valid_orient(orientation) || x == x0 || iters < 0) return eq_fail(EQ_ERR_INVALID, "bad diffuse arguments");
+    LinSolveReq r = diffuse_req(h, orientation, x, x0, diffusion);
+    return lin_solve(h, &r, 1, iters);
+}
+
+int eq_op_project(eq_fluid *h, int vx_field, int vy_field, int p_field, int div_field, int64_t iters) {
+    NEED(h);
+    float *vx, *vy, *p, *div;
+    TRY(f32_field(h, vx_field, &vx));
+    TRY(f32_field(h, vy_field, &vy));
+    TRY(f32_field(h, p_field, &p));
+    TRY(f32_field(h, div_field, &div));
+    if (vx == vy || vx == p || vx == div || vy == p || vy == div || p == div || iters < 0)
+        return eq_fail(EQ_ERR_INVALID, "project needs four distinct fields");
+    return project(h, vx, vy, p, div, iters);
+}
+
+int eq_op_advect(eq_fluid *h, int orientation, int d_field, int d0_field, int vx_field, int vy_field) {
+    NEED(h);
+    float *d, *d0, *vx, *vy;
+    TRY(f32_field(h, d_field, &d));
+    TRY(f32_field(h, d0_field, &d0));
+    TRY(f32_field(h, vx_field, &vx));
+    TRY(f32_field(h, vy_field, &vy));
+    if (!valid_orient(orientation) || d == d0 || d == vx || d == vy) return eq_fail(EQ_ERR_INVALID, "bad advect arguments");
+    return advect(h, orientation, d, d0, 0, nullptr, nullptr, vx, vy);
+}
+
+int eq_divergence_l2(eq_fluid *h, int vx_field, int vy_field, double *out) {
+    NEED(h);
+    float *vx, *vy;
+    TRY(f32_field(h, vx_field, &vx));
+    TRY(f32_field(h, vy_field, &vy));
+    if (!out) return eq_fail(EQ_ERR_INVALID, "null out");
+    double *d = nullptr;
+    CU(cudaMalloc(&d, sizeof(double)));
+    CU(cudaMemsetAsync(d, 0, sizeof(double), h->stream));
+    EQ_LAUNCH(k_divergence_sq, row_grid(h, h->L.N - 2), 256, 0, h->stream, vx, vy, d, h->L);
+    int r = check_launch("k_divergence_sq");
+    double v = 0.0;
+    if (r == EQ_OK && cudaMemcpyAsync(&v, d, sizeof(double), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) r = EQ_ERR_CUDA;
+    if (r == EQ_OK && cudaStreamSynchronize(h->stream) != cudaSuccess) r = EQ_ERR_CUDA;
+    cudaFree(d);
+    if (r != EQ_OK) return eq_fail(r, "eq_divergence_l2 failed");
+    *out = sqrt(v);
+    return EQ_OK;
+}
+
+int eq_set_stream(eq_fluid *h, void *cuda_stream) {
+    NEED(h);
+    CU(cudaStreamSynchronize(h->stream));
+    h->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->own_stream;
+    return EQ_OK;
+}
+
+int eq_timer_start(eq_fluid *h) {
+    NEED(h);
+    CU(cudaEventRecord(h->ev0, h->stream));
+    return EQ_OK;
+}
+
+int eq_timer_stop(eq_fluid *h, float *ms) {
+    NEED(h);
+    if (!ms) return eq_fail(EQ_ERR_INVALID, "null out");
+    CU(cudaEventRecord(h->ev1, h->stream));
+    CU(cudaEventSynchronize(h->ev1));
+    CU(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+    return EQ_OK;
+}
+
+int eq_profile_enable(eq_fluid *h, int on) {
+    NEED(h);
+    TRY(prof_collect(h));
+    h->prof_on = on != 0;
+    return EQ_OK;
+}
+
+int eq_profile_reset(eq_fluid *h) {
+    NEED(h);
+    TRY(prof_collect(h));
+    memset(h->prof_ms, 0, sizeof(h->prof_ms));
+    memset(h->prof_launches, 0, sizeof(h->prof_launches));
+    h->prof_cell_iters = 0;
+    h->prof_steps = 0;
+    return EQ_OK;
+}
+
+int eq_profile_get(eq_fluid *h, EqProfile *out) {
+    NEED(h);
+    if (!out) return eq_fail(EQ_ERR_INVALID, "null out");
+    TRY(prof_collect(h));
+    out->lin_solve_ms = h->prof_ms[CAT_LS];
+    out->lin_solve_launches = h->prof_launches[CAT_LS];
+    out->lin_solve_cell_iters = h->prof_cell_iters;
+    out->advect_ms = h->prof_ms[CAT_ADV];
+    out->advect_launches = h->prof_launches[CAT_ADV];
+    out->project_ms = h->prof_ms[CAT_PROJ];
+    out->project_launches = h->prof_launches[CAT_PROJ];
+    out->boundary_ms = h->prof_ms[CAT_BND];
+    out->boundary_launches = h->prof_launches[CAT_BND];
+    out->other_ms = h->prof_ms[CAT_OTHER];
+    out->other_launches = h->prof_launches[CAT_OTHER];
+    out->steps = h->prof_steps;
+    return EQ_OK;
+}
+
+int eq_host_alloc(void **out, size_t bytes) {
+    if (!out) return eq_fail(EQ_ERR_INVALID, "null out");
+    CU(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+    return EQ_OK;
+}
+
+int eq_host_free(void *p) {
+    if (p) CU(cudaFreeHost(p));
+    return EQ_OK;
+}
+
+int eq_l2_flush(eq_fluid *h) {
+    NEED(h);
+    if (!h->l2buf) {
+        h->l2bytes = (size_t)256 << 20;   // > 126 MB of L2
+        CU(cudaMalloc(&h->l2buf, h->l2bytes));
+    }
+    CU(cudaMemsetAsync(h->l2buf, 0, h->l2bytes, h->stream));
+    return EQ_OK;
+}
+
+int eq_comm_unique_id(uint8_t id[128]) {
+    if (!id) return eq_fail(EQ_ERR_INVALID, "null id");
+    memset(id, 0, 128);
+    return eq_fail(EQ_ERR_COMM, "multi-GPU slabs are not implemented in this build");
+}
+
+}  // extern "C"

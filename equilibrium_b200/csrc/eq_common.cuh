@@ -1,0 +1,77 @@
+// eq_common.cuh -- shared device helpers and the HBM data layout.
+//
+// Layout of one field in HBM (DESIGN.md "Data layout"):
+//   float buf[(N + EQ_ROW_PAD) * P],  P = round_up(N, 32)
+//   cell (x, y) lives at buf[x + y * P]  (row-major like idx!, fluid.rs:31-35)
+// Rows N..N+EQ_ROW_PAD-1 and columns N..P-1 are zero padding that no kernel
+// ever writes a non-padding value to; they let the wavefront kernel stage
+// 34-row x 32-column tiles with 16-byte cp.async and no bounds checks.
+#pragma once
+#include <stdint.h>
+
+#include "../../include/equilibrium_cuda.h"
+
+#ifdef EQ_HOST_EMU
+// tests/emu: same sources compiled with g++ against a host SIMT emulator (tests only)
+#include "cuda_emu.h"
+#else
+#include <cuda_runtime.h>
+#define EQ_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#define EQ_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
+
+#define EQ_ROW_PAD 32
+
+// cells_type / derived per-cell codes (one byte per cell, same pitch P):
+//   bits 0-1  AdjustRow fix-up:    0 none, 1 take -x[i-1,j], 2 take -x[i+1,j]   (fluid.rs:151-164)
+//   bits 2-3  AdjustColumn fix-up: 0 none, 1 take -x[i,j-1], 2 take -x[i,j+1]   (fluid.rs:165-178)
+//   bit 7     the cell itself is DefaultWall
+#define EQ_CODE_ROW_LEFT 1u
+#define EQ_CODE_ROW_RIGHT 2u
+#define EQ_CODE_COL_UP (1u << 2)
+#define EQ_CODE_COL_DOWN (2u << 2)
+#define EQ_CODE_WALL 0x80u
+
+struct EqLayout {
+    int N;      // grid is N x N
+    int P;      // row pitch in elements
+    int rows;   // allocated rows = N + EQ_ROW_PAD
+};
+
+#ifndef EQ_HOST_EMU
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_volatile_s32(const int *p) {
+    int v;
+    asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// 16-byte async copy global -> shared, L2 only (.cg): the data may have been
+// written by another SM moments ago, so L1 must not serve it.
+__device__ __forceinline__ void cp_async_16(void *smem, const void *gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+#endif  // !EQ_HOST_EMU
+
+// The Gauss-Seidel update of fluid.rs:315-320 with the reference's expression
+// tree: (x0 + a * (((right + left) + down) + up)) * c_recip, every operation
+// individually rounded (no FMA: rustc never contracts).
+__device__ __forceinline__ float gs_update(float x0, float right, float left, float down, float up,
+                                           float a, float c_recip) {
+    float s = __fadd_rn(right, left);
+    s = __fadd_rn(s, down);
+    s = __fadd_rn(s, up);
+    return __fmul_rn(__fadd_rn(x0, __fmul_rn(a, s)), c_recip);
+}

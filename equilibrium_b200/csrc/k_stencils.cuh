@@ -1,0 +1,290 @@
+// k_stencils.cuh -- the non-iterative kernels of Fluid::step (fluid.rs:437-524):
+// mask-derived tables, set_boundaries (sparse), divergence, gradient subtract,
+// semi-Lagrangian advect, point sources, init.
+//
+// Every floating-point expression uses the explicit round-to-nearest intrinsics
+// in the reference's evaluation order, so nvcc can neither contract to FMA nor
+// reassociate (rustc does neither).
+#pragma once
+#include "eq_common.cuh"
+
+// ---------------------------------------------------------------------------
+// Mask-derived tables.  set_boundaries (fluid.rs:252-272) visits every cell but
+// only changes NoWall cells that touch a wall (AdjustRow/AdjustColumn) or frame
+// cells (Passive).  We precompute, per cell, which neighbour it mirrors.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned eq_cell_code(const uint8_t *cells, int i, int j, int N, int P) {
+    if (cells[i + (size_t)j * P]) return EQ_CODE_WALL;                 // fluid.rs:141-143
+    const int il = max(i - 1, 0), ir = min(i + 1, N - 1);              // :147-148 (clamped)
+    const int ju = max(j - 1, 0), jd = min(j + 1, N - 1);              // :145-146
+    unsigned code = 0;
+    if (cells[ir + (size_t)j * P]) code |= EQ_CODE_ROW_RIGHT;          // right assigned last => wins (:158-163)
+    else if (cells[il + (size_t)j * P]) code |= EQ_CODE_ROW_LEFT;      // :152-157
+    if (cells[i + (size_t)ju * P]) code |= EQ_CODE_COL_UP;             // up assigned last => wins (:172-177)
+    else if (cells[i + (size_t)jd * P]) code |= EQ_CODE_COL_DOWN;      // :166-171
+    return code;
+}
+
+// pass 0: codes + row/column "has fluid" flags + counts; pass 1: fill the lists
+__global__ void k_build_codes(const uint8_t *__restrict__ cells, uint8_t *__restrict__ codes,
+                              uint8_t *row_fluid, uint8_t *col_fluid, unsigned *counts,
+                              uint2 *row_list, uint2 *col_list, int pass, EqLayout L) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    if (i >= L.N) return;
+    const unsigned code = eq_cell_code(cells, i, j, L.N, L.P);
+    const unsigned o = (unsigned)i + (unsigned)j * (unsigned)L.P;
+    if (pass == 0) {
+        codes[o] = (uint8_t)code;
+        if (!(code & EQ_CODE_WALL)) {
+            row_fluid[j] = 1;
+            col_fluid[i] = 1;
+        }
+        if (code & 3u) atomicAdd(&counts[0], 1u);
+        if (code & 12u) atomicAdd(&counts[1], 1u);
+    } else {
+        if (code & 3u) {
+            const unsigned slot = atomicAdd(&counts[2], 1u);
+            row_list[slot] = make_uint2(o, (code & 3u) == EQ_CODE_ROW_RIGHT ? o + 1u : o - 1u);
+        }
+        if (code & 12u) {
+            const unsigned slot = atomicAdd(&counts[3], 1u);
+            col_list[slot] = make_uint2(o, (code & 12u) == EQ_CODE_COL_UP ? o - (unsigned)L.P : o + (unsigned)L.P);
+        }
+    }
+}
+
+// 4 corners (fluid.rs:265-271) from the *current* frame values.
+__device__ __forceinline__ void eq_corners(float *x, int N, int P) {
+    const size_t last = (size_t)(N - 1) * P;
+    const size_t prev = (size_t)(N - 2) * P;
+    x[0] = __fmul_rn(0.5f, __fadd_rn(x[1], x[P]));
+    x[last] = __fmul_rn(0.5f, __fadd_rn(x[last + 1], x[prev]));
+    x[N - 1] = __fmul_rn(0.5f, __fadd_rn(x[N - 2], x[(size_t)P + N - 1]));
+    x[last + N - 1] = __fmul_rn(0.5f, __fadd_rn(x[last + N - 2], x[prev + N - 1]));
+}
+
+__global__ void k_corners(float *x, EqLayout L) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) eq_corners(x, L.N, L.P);
+}
+
+// set_boundaries(AdjustRow | AdjustColumn): x[dst] = -x[src] for the listed
+// cells.  Sources are wall cells (never a dst), so the pass is order-free.
+// Frame cells are walls, so the corners can be done by the same launch.
+__global__ void k_bnd_list(float *x, const uint2 *__restrict__ list, unsigned n, EqLayout L) {
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) {
+        const uint2 e = list[t];
+        x[e.x] = -x[e.y];
+    }
+    if (t == 0) eq_corners(x, L.N, L.P);
+}
+
+// set_boundaries(Passive) (fluid.rs:179-187 + quirk Q6) and the corners.  The
+// corner thread evaluates the post-copy frame values itself (it only reads
+// interior cells, or frame cells nobody writes), so one launch suffices.
+__global__ void k_bnd_passive(float *x, const uint8_t *__restrict__ row_fluid,
+                              const uint8_t *__restrict__ col_fluid, EqLayout L) {
+    const int N = L.N, P = L.P;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;   // 1 .. N-2
+    if (t >= 1 && t <= N - 2) {
+        if (col_fluid[t]) {
+            x[t] = x[t + (size_t)P];
+            x[t + (size_t)(N - 1) * P] = x[t + (size_t)(N - 2) * P];
+        }
+        if (row_fluid[t]) {
+            x[(size_t)t * P] = x[(size_t)t * P + 1];
+            x[(size_t)t * P + N - 1] = x[(size_t)t * P + N - 2];
+        }
+    }
+    if (t == 0) {
+        const size_t r1 = P, rl = (size_t)(N - 1) * P, rp = (size_t)(N - 2) * P;
+        const bool c1 = col_fluid[1], cl = col_fluid[N - 2], w1 = row_fluid[1], wl = row_fluid[N - 2];
+        const float a00 = c1 ? x[r1 + 1] : x[1];                 // x[1,0] after the copy
+        const float b00 = w1 ? x[r1 + 1] : x[r1];                // x[0,1]
+        const float a0l = c1 ? x[rp + 1] : x[rl + 1];            // x[1,N-1]
+        const float b0l = wl ? x[rp + 1] : x[rp];                // x[0,N-2]
+        const float al0 = cl ? x[r1 + N - 2] : x[N - 2];         // x[N-2,0]
+        const float bl0 = w1 ? x[r1 + N - 2] : x[r1 + N - 1];    // x[N-1,1]
+        const float all_ = cl ? x[rp + N - 2] : x[rl + N - 2];   // x[N-2,N-1]
+        const float bll = wl ? x[rp + N - 2] : x[rp + N - 1];    // x[N-1,N-2]
+        x[0] = __fmul_rn(0.5f, __fadd_rn(a00, b00));
+        x[rl] = __fmul_rn(0.5f, __fadd_rn(a0l, b0l));
+        x[N - 1] = __fmul_rn(0.5f, __fadd_rn(al0, bl0));
+        x[rl + N - 1] = __fmul_rn(0.5f, __fadd_rn(all_, bll));
+    }
+}
+
+// ---------------------------------------------------------------------------
+// project, part 1 (fluid.rs:339-349): divergence and p = 0 on the interior.
+// ---------------------------------------------------------------------------
+__global__ void k_divergence(const float *__restrict__ vx, const float *__restrict__ vy,
+                             float *__restrict__ div, float *__restrict__ p, EqLayout L) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y + 1;
+    if (i < 1 || i > L.N - 2) return;
+    const size_t o = (size_t)i + (size_t)j * L.P;
+    float t = __fsub_rn(vx[o + 1], vx[o - 1]);
+    t = __fadd_rn(t, vy[o + L.P]);
+    t = __fsub_rn(t, vy[o - L.P]);
+    div[o] = __fdiv_rn(__fmul_rn(-0.5f, t), (float)L.N);
+    p[o] = 0.0f;
+}
+
+// project, part 2 (fluid.rs:364-371): subtract the pressure gradient.
+__global__ void k_gradient(float *__restrict__ vx, float *__restrict__ vy,
+                           const float *__restrict__ p, EqLayout L) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y + 1;
+    if (i < 1 || i > L.N - 2) return;
+    const size_t o = (size_t)i + (size_t)j * L.P;
+    const float nf = (float)L.N;
+    vx[o] = __fsub_rn(vx[o], __fmul_rn(__fmul_rn(0.5f, __fsub_rn(p[o + 1], p[o - 1])), nf));
+    vy[o] = __fsub_rn(vy[o], __fmul_rn(__fmul_rn(0.5f, __fsub_rn(p[o + L.P], p[o - L.P])), nf));
+}
+
+// ---------------------------------------------------------------------------
+// advect (fluid.rs:378-432).  One CTA per row because of the row-serial `break`
+// (quirk Q4): the first cell f of row j whose back-traced sample leaves the grid
+// copies its already-updated left neighbour and every cell after it keeps its
+// stale destination value.  The flag depends on the velocity at the cell only,
+// so: pass 1 = min-reduce f over the row, pass 2 = cells < f normal, cell f copy.
+// NF fields that share the velocity field (vx and vy self-advection,
+// fluid.rs:469-489) are advected by one launch.
+// ---------------------------------------------------------------------------
+struct AdvSample {
+    float s0, s1, t0, t1;
+    unsigned i0, i1, j0, j1;
+    bool flagged;
+};
+
+__device__ __forceinline__ float eq_clamp_rust(float v, float lo, float hi) {
+    if (v < lo) v = lo;     // f32::clamp: NaN stays NaN
+    if (v > hi) v = hi;
+    return v;
+}
+
+__device__ __forceinline__ AdvSample eq_backtrace(int i, int j, float u, float v, float dtx, float nf, int N) {
+    AdvSample r;
+    float x = __fsub_rn((float)i, __fmul_rn(dtx, u));                  // :400
+    float y = __fsub_rn((float)j, __fmul_rn(dtx, v));                  // :401 (delta_t_y == delta_t_x)
+    x = eq_clamp_rust(x, 0.5f, __fsub_rn(nf, 1.0f));                   // :403
+    y = eq_clamp_rust(y, 0.5f, __fsub_rn(nf, 1.0f));                   // :404
+    const float i0 = floorf(x), i1 = __fadd_rn(i0, 1.0f);              // :406-407
+    const float j0 = floorf(y), j1 = __fadd_rn(j0, 1.0f);              // :409-410
+    r.s1 = __fsub_rn(x, i0);                                           // :412
+    r.s0 = __fsub_rn(1.0f, r.s1);
+    r.t1 = __fsub_rn(y, j0);
+    r.t0 = __fsub_rn(1.0f, r.t1);
+    // `as u32` saturates and maps NaN to 0 (:417-418); idx! then clamps to N-1
+    r.i0 = min(__float2uint_rz(i0), (unsigned)(N - 1));
+    r.i1 = min(__float2uint_rz(i1), (unsigned)(N - 1));
+    r.j0 = min(__float2uint_rz(j0), (unsigned)(N - 1));
+    r.j1 = min(__float2uint_rz(j1), (unsigned)(N - 1));
+    r.flagged = (i1 >= nf) || (j1 >= nf);                              // :420
+    return r;
+}
+
+__device__ __forceinline__ float eq_bilinear(const AdvSample &r, const float *__restrict__ d0, int P) {
+    const float a = d0[r.i0 + (size_t)r.j0 * P], b = d0[r.i0 + (size_t)r.j1 * P];
+    const float c = d0[r.i1 + (size_t)r.j0 * P], d = d0[r.i1 + (size_t)r.j1 * P];
+    const float l = __fadd_rn(__fmul_rn(r.t0, a), __fmul_rn(r.t1, b));
+    const float h = __fadd_rn(__fmul_rn(r.t0, c), __fmul_rn(r.t1, d));
+    return __fadd_rn(__fmul_rn(r.s0, l), __fmul_rn(r.s1, h));          // :424-428
+}
+
+template <int NF>
+__global__ void __launch_bounds__(256) k_advect(float *__restrict__ dA, const float *__restrict__ d0A,
+                                                float *__restrict__ dB, const float *__restrict__ d0B,
+                                                const float *__restrict__ vx, const float *__restrict__ vy,
+                                                float dt, EqLayout L) {
+    const int N = L.N, P = L.P;
+    const int j = blockIdx.x + 1;
+    const float nf = (float)N;
+    const float dtx = __fmul_rn(dt, (float)(N - 2));                   // :390
+    const size_t row = (size_t)j * P;
+    __shared__ int s_first;
+    if (threadIdx.x == 0) s_first = N;
+    __syncthreads();
+    int mine = N;
+    for (int i = 1 + threadIdx.x; i <= N - 2; i += blockDim.x) {
+        const AdvSample r = eq_backtrace(i, j, vx[row + i], vy[row + i], dtx, nf, N);
+        if (r.flagged) { mine = i; break; }                            // first one of this thread
+    }
+    mine = min(mine, __shfl_xor_sync(0xffffffffu, mine, 16));
+    mine = min(mine, __shfl_xor_sync(0xffffffffu, mine, 8));
+    mine = min(mine, __shfl_xor_sync(0xffffffffu, mine, 4));
+    mine = min(mine, __shfl_xor_sync(0xffffffffu, mine, 2));
+    mine = min(mine, __shfl_xor_sync(0xffffffffu, mine, 1));
+    if ((threadIdx.x & 31) == 0 && mine < N) atomicMin(&s_first, mine);
+    __syncthreads();
+    const int f = s_first;                                             // N => no break in this row
+    const int last = min(f, N - 2);
+    for (int i = 1 + threadIdx.x; i <= last; i += blockDim.x) {
+        const int src = (i == f) ? i - 1 : i;                          // :421 copy of the updated left cell
+        float a, b = 0.f;
+        if (src == 0) {                                                // f == 1: the frame cell, untouched
+            a = dA[row];
+            if (NF == 2) b = dB[row];
+        } else {
+            const AdvSample r = eq_backtrace(src, j, vx[row + src], vy[row + src], dtx, nf, N);
+            a = eq_bilinear(r, d0A, P);
+            if (NF == 2) b = eq_bilinear(r, d0B, P);
+        }
+        dA[row + i] = a;
+        if (NF == 2) dB[row + i] = b;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// sources and initial condition
+// ---------------------------------------------------------------------------
+// add_density (fluid.rs:120-124) / add_velocity (fluid.rs:127-131) as one stream-ordered launch
+__global__ void k_add_source(float *density, float *scratch, float *vx, float *vy, unsigned o,
+                             float dd, float dvx, float dvy, int what) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        if (what & 1) {
+            density[o] = __fadd_rn(density[o], dd);
+            scratch[o] = __fadd_rn(scratch[o], dd);
+        }
+        if (what & 2) {
+            vx[o] = __fadd_rn(vx[o], dvx);
+            vy[o] = __fadd_rn(vy[o], dvy);
+        }
+    }
+}
+
+// field[x,y] += amount on [x0,x1) x [y0,y1)   (init_velocities :542-548, init_density :534-538)
+__global__ void k_add_rect(float *f, int x0, int y0, int x1, int y1, float amount, EqLayout L) {
+    const int i = x0 + blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = y0 + blockIdx.y;
+    if (i < x1 && j < y1) {
+        const size_t o = (size_t)i + (size_t)j * L.P;
+        f[o] = __fadd_rn(f[o], amount);
+    }
+}
+
+// cells[x,y] = value on [x0,x1) x [y0,y1) (init_walls :552-570, fill_obstacle :610-619; caller clamps)
+__global__ void k_set_cells_rect(uint8_t *cells, int x0, int y0, int x1, int y1, uint8_t value, EqLayout L) {
+    const int i = x0 + blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = y0 + blockIdx.y;
+    if (i < x1 && j < y1) cells[(size_t)i + (size_t)j * L.P] = value;
+}
+
+// sum over the interior of div^2 with the stencil of fluid.rs:341-345 (diagnostic only)
+__global__ void k_divergence_sq(const float *__restrict__ vx, const float *__restrict__ vy, double *out,
+                                EqLayout L) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y + 1;
+    double v = 0.0;
+    if (i >= 1 && i <= L.N - 2) {
+        const size_t o = (size_t)i + (size_t)j * L.P;
+        float t = __fsub_rn(vx[o + 1], vx[o - 1]);
+        t = __fadd_rn(t, vy[o + L.P]);
+        t = __fsub_rn(t, vy[o - L.P]);
+        const float d = __fdiv_rn(__fmul_rn(-0.5f, t), (float)L.N);
+        v = (double)d * (double)d;
+    }
+    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(out, v);
+}

@@ -1,0 +1,205 @@
+// tests/emu/cuda_emu.h -- TEST INFRASTRUCTURE: a tiny host-side SIMT emulator.
+//
+// Compiling equilibrium_b200/csrc/eq_api.cu with g++ -DEQ_HOST_EMU swaps the
+// CUDA runtime and the device intrinsics for the stand-ins below, so the SAME
+// kernel sources and the SAME C-ABI host logic run on a CPU-only box:
+//   * kernels without intra-block communication run as plain loops;
+//   * kernels that use __syncthreads / __shfl_* / inter-CTA flags run with one
+//     OS thread per CUDA thread, std::barrier for the warp and the block, and
+//     all CTAs of the persistent wavefront kernel concurrently (so the ticket /
+//     release-acquire flag protocol is exercised under real concurrency).
+// It is slow and only meant for grids up to ~128^2.  It is NOT a CPU fallback:
+// nothing in the equilibrium_b200 package loads it; only tests/ does.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <barrier>
+#include <functional>
+#include <memory>
+#include <thread>
+#include <vector>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline __attribute__((always_inline))
+#define __launch_bounds__(...)
+#define __shared__ static
+#define __align__(n) alignas(n)
+
+struct uint3_emu { unsigned x, y, z; };
+struct dim3 {
+    unsigned x, y, z;
+    dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
+};
+struct uint2 { unsigned x, y; };
+static inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
+struct alignas(16) float4 { float x, y, z, w; };
+
+namespace eq_emu {
+struct WarpState {
+    std::barrier<> bar;
+    uint64_t xch[32];
+    explicit WarpState(int n) : bar(n) {}
+};
+struct BlockState {
+    std::barrier<> bar;
+    std::vector<std::unique_ptr<WarpState>> warps;
+    std::vector<unsigned char> dyn_smem;
+    explicit BlockState(int n) : bar(n) {}
+};
+struct Ctx {
+    uint3_emu tid, bid;
+    dim3 bdim, gdim;
+    BlockState *block = nullptr;
+    WarpState *warp = nullptr;
+    int lane = 0;
+};
+extern thread_local Ctx ctx;
+enum Mode { SEQUENTIAL = 0, BLOCK_THREADS = 1, CONCURRENT_GRID = 2 };
+Mode mode_for(const char *kernel_name);
+void launch(const char *name, dim3 grid, dim3 block, size_t smem, const std::function<void()> &body);
+inline unsigned char *dyn_smem() { return ctx.block->dyn_smem.data(); }
+}  // namespace eq_emu
+
+#define threadIdx (eq_emu::ctx.tid)
+#define blockIdx (eq_emu::ctx.bid)
+#define blockDim (eq_emu::ctx.bdim)
+#define gridDim (eq_emu::ctx.gdim)
+
+#define EQ_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    eq_emu::launch(#kernel, dim3(grid), dim3(block), (size_t)(smem), [&]() { kernel(__VA_ARGS__); })
+#define EQ_DYN_SMEM(name) unsigned char *name = eq_emu::dyn_smem()
+
+// ---- warp / block primitives ------------------------------------------------
+static inline void __syncwarp(unsigned = 0xffffffffu) {
+    if (eq_emu::ctx.warp) eq_emu::ctx.warp->bar.arrive_and_wait();
+}
+static inline void __syncthreads() {
+    if (eq_emu::ctx.block) eq_emu::ctx.block->bar.arrive_and_wait();
+}
+template <typename T>
+static inline T eq_emu_exchange(T v, int src_lane) {
+    static_assert(sizeof(T) <= 8, "shuffle payload");
+    eq_emu::WarpState *w = eq_emu::ctx.warp;
+    uint64_t raw = 0;
+    memcpy(&raw, &v, sizeof(T));
+    w->xch[eq_emu::ctx.lane] = raw;
+    w->bar.arrive_and_wait();
+    const uint64_t got = w->xch[src_lane];
+    w->bar.arrive_and_wait();
+    T out;
+    memcpy(&out, &got, sizeof(T));
+    return out;
+}
+template <typename T>
+static inline T __shfl_up_sync(unsigned, T v, int d) {
+    const int l = eq_emu::ctx.lane;
+    return eq_emu_exchange(v, l >= d ? l - d : l);
+}
+template <typename T>
+static inline T __shfl_down_sync(unsigned, T v, int d) {
+    const int l = eq_emu::ctx.lane;
+    return eq_emu_exchange(v, l + d < 32 ? l + d : l);
+}
+template <typename T>
+static inline T __shfl_xor_sync(unsigned, T v, int m) {
+    return eq_emu_exchange(v, eq_emu::ctx.lane ^ m);
+}
+template <typename T>
+static inline T __shfl_sync(unsigned, T v, int src) {
+    return eq_emu_exchange(v, src);
+}
+
+// ---- memory model stand-ins --------------------------------------------------
+static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+static inline void __nanosleep(unsigned) { std::this_thread::yield(); }
+static inline unsigned ld_acquire_u32(const unsigned *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+static inline void st_release_u32(unsigned *p, unsigned v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+static inline int ld_volatile_s32(const int *p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
+static inline void cp_async_16(void *smem, const void *gmem) { memcpy(smem, gmem, 16); }
+static inline void cp_async_commit() {}
+template <int N>
+static inline void cp_async_wait() {}
+static inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+static inline int atomicMin(int *p, int v) {
+    int old = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (old > v && !__atomic_compare_exchange_n(p, &old, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {
+    }
+    return old;
+}
+static inline double atomicAdd(double *p, double v) {
+    uint64_t *u = reinterpret_cast<uint64_t *>(p);
+    uint64_t old = __atomic_load_n(u, __ATOMIC_RELAXED);
+    for (;;) {
+        double d;
+        memcpy(&d, &old, 8);
+        d += v;
+        uint64_t nu;
+        memcpy(&nu, &d, 8);
+        if (__atomic_compare_exchange_n(u, &old, nu, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) return d - v;
+    }
+}
+
+// ---- arithmetic intrinsics (compile with -ffp-contract=off) ------------------
+static inline float __fadd_rn(float a, float b) { return a + b; }
+static inline float __fsub_rn(float a, float b) { return a - b; }
+static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline float __fdiv_rn(float a, float b) { return a / b; }
+static inline unsigned __float2uint_rz(float v) {
+    if (!(v > 0.0f)) return 0u;
+    if (v >= 4294967296.0f) return 0xFFFFFFFFu;
+    return (unsigned)v;
+}
+using std::max;
+using std::min;
+
+// ---- the sliver of the CUDA runtime that eq_api.cu uses ----------------------
+typedef int cudaError_t;
+enum { cudaSuccess = 0 };
+typedef struct eq_emu_stream *cudaStream_t;
+typedef struct eq_emu_event { double t; } *cudaEvent_t;
+enum { cudaStreamNonBlocking = 1, cudaHostAllocDefault = 0 };
+enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
+enum { cudaDevAttrMultiProcessorCount = 16, cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+
+static inline const char *cudaGetErrorString(cudaError_t) { return "emulated"; }
+static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+static inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
+cudaError_t cudaDeviceGetAttribute(int *v, int attr, int dev);
+static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = nullptr; return cudaSuccess; }
+static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaEventCreate(cudaEvent_t *e);
+cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t);
+static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b);
+cudaError_t cudaEventDestroy(cudaEvent_t e);
+template <typename T>
+static inline cudaError_t cudaMalloc(T **p, size_t bytes) {
+    *p = static_cast<T *>(aligned_alloc(128, (bytes + 127) / 128 * 128 + 128));
+    return *p ? cudaSuccess : 2;
+}
+static inline cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
+static inline cudaError_t cudaMemsetAsync(void *p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
+static inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t) {
+    memcpy(d, s, n);
+    return cudaSuccess;
+}
+static inline cudaError_t cudaMemcpy2DAsync(void *d, size_t dp, const void *s, size_t sp, size_t w, size_t h,
+                                            cudaMemcpyKind, cudaStream_t) {
+    for (size_t r = 0; r < h; ++r) memcpy(static_cast<char *>(d) + r * dp, static_cast<const char *>(s) + r * sp, w);
+    return cudaSuccess;
+}
+static inline cudaError_t cudaHostAlloc(void **p, size_t n, unsigned) { *p = malloc(n); return *p ? cudaSuccess : 2; }
+static inline cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
+template <typename F>
+static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
+template <typename F>
+static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, F, int, size_t) { *n = 1; return cudaSuccess; }
