@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the stable-fluids step (Fluid::step, fluid.rs:437-524).
+
+    python bench.py --gpus N --steps K --warmup W [--workload c4] [--impl reference]
+
+A "step" is one frame of Fluid::step over the whole grid.  metric = grid
+cell-updates/s = size^2 * frames / time (BASELINE.json / SURVEY.md 8d).
+
+Workloads (BASELINE.json configs):
+  c4 (default) 16384^2, 20 GS iterations, 16 random rectangles (seed 16384), exact mode
+  c3           4096^2,  40 GS iterations, 64 random rectangles (seed 4096),  exact mode
+  c2           1024^2,  20 GS iterations, no obstacles
+The same workload is used for every --gpus value so the driver's scaling series is a
+strong-scaling series (row slabs, halo exchange per sweep).
+
+JSON line keys beyond the base contract: roofline (dominant kernel = lin_solve),
+cpu_baseline (the CPU oracle on one host core, bounded sample), red_black (the fast
+path on the same workload), clocks, e2e, gpu_launches.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "c2": dict(size=1024, k=20, rects=0, seed=1024, cpu_rows=1024),
+    "c3": dict(size=4096, k=40, rects=64, seed=4096, cpu_rows=512),
+    "c4": dict(size=16384, k=20, rects=16, seed=16384, cpu_rows=512),
+}
+METRIC = "grid cell-updates/sec per frame"
+UNIT = "cell-updates/s"
+
+
+def random_rects(n, count, seed):
+    """SURVEY.md 8d generator (same as tests/parity.py)."""
+    rng = np.random.default_rng(seed)
+    out = []
+    lo, hi = max(1, n // 64), max(2, n // 16)
+    for _ in range(count):
+        w, h = int(rng.integers(lo, hi + 1)), int(rng.integers(lo, hi + 1))
+        x0, y0 = int(rng.integers(1, n - 2 - w + 1)), int(rng.integers(1, n - 2 - h + 1))
+        out.append((x0, y0, x0 + w, y0 + h))
+    return out
+
+
+def impulses(n, frames, seed=0):
+    rng = np.random.default_rng(seed)
+    return [(fr, n // 2, n // 2, float(np.float32(rng.uniform(-2 * n, 2 * n))),
+             float(np.float32(rng.uniform(-2 * n, 2 * n)))) for fr in range(frames)]
+
+
+def algorithmic_bytes_per_cell(k):
+    """SURVEY.md 8d streaming model: 60K + 112 bytes per cell per frame."""
+    return 60 * k + 112
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device=0):
+        self.rows, self.proc, self.device = [], None, device
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(wl, steps=1):
+    """The CPU oracle (oracle/fluid_ref.c, the line-by-line restatement of fluid.rs) on ONE
+    host core -- the reference's step() is single-threaded (renderer.rs:125-128) -- on a
+    bounded sample: `steps` frames of a full-width row band of the workload."""
+    from oracle import loader as O
+    n, k = wl["size"], wl["k"]
+    rows = min(n, wl["cpu_rows"])
+    f = O.RefFluid(n, 0.02, k, 0.0, 0.001, rows=rows)
+    for (x0, y0, x1, y1) in random_rects(n, wl["rects"], wl["seed"]):
+        f.fill_rect(x0, min(y0, rows - 1), x1, min(y1, rows - 1))
+    f.add_velocity(n // 2, rows // 2, 50.0, -30.0)
+    t0 = time.perf_counter()
+    f.step(steps)
+    dt = time.perf_counter() - t0
+    sample = (f"{steps} frame(s) of a {n}x{rows} row band (full-width rows, K={k}); "
+              f"oracle/fluid_ref.c, gcc -O2 -ffp-contract=off, single thread")
+    return {"value": n * rows * steps / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": sample, "seconds": dt, "host_cpus": os.cpu_count()}
+
+
+def run_reference_arm(args, wl, rank):
+    if rank != 0:
+        return
+    vals = []
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        cpu_baseline(wl, 1)
+    t_all = 0.0
+    res = None
+    for _ in range(max(1, args.steps)):
+        res = cpu_baseline(wl, 1)
+        vals.append(res["value"])
+        t_all += res["seconds"]
+    v = float(np.mean(vals))
+    res["value"] = v
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / max(1, args.steps),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": wl_name(wl), "size": wl["size"], "gs_iterations": wl["k"],
+                   "rectangles": wl["rects"], "note": "CPU oracle port of fluid.rs; the Rust reference cannot be built here (no cargo)"},
+        "cpu_baseline": res,
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def wl_name(wl):
+    return f"{wl['size']}^2 stable-fluids step, {wl['k']} GS iterations, {wl['rects']} random rectangles (seed {wl['seed']})"
+
+
+def pinned_array(lib, shape, dtype):
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = C.c_void_p()
+    rc = lib.eq_host_alloc(C.byref(p), n)
+    if rc != 0:
+        raise RuntimeError("eq_host_alloc failed")
+    buf = (C.c_char * n).from_address(p.value)
+    return np.frombuffer(buf, dtype=dtype).reshape(shape), p
+
+
+def build_fluid(wl, mode, device=0):
+    from equilibrium_b200 import Fluid, FluidConfigs, Rectangle, SimulationConfigs
+    n = wl["size"]
+    f = Fluid(FluidConfigs(diffusion=0.0, viscousity=0.001), SimulationConfigs(0.02, wl["k"], n),
+              mode=mode, device=device)
+    for (x0, y0, x1, y1) in random_rects(n, wl["rects"], wl["seed"]):
+        f.fill_obstacle(Rectangle((x0, y0), (x1, y1), n))
+    return f
+
+
+def time_device_resident(f, n, steps, warmup, seed):
+    imp = impulses(n, warmup + steps, seed)
+    f.step_n(warmup, imp[:warmup])
+    f.sync()
+    timed = [(fr - warmup, x, y, ax, ay) for (fr, x, y, ax, ay) in imp[warmup:]]
+    f.timer_start()
+    f.step_n(steps, timed)
+    ms = f.timer_stop()
+    f.sync()
+    return ms
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-extras", action="store_true", help="skip red-black / e2e / cpu legs (profiling runs)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    wl = WORKLOADS[args.workload]
+    n, k = wl["size"], wl["k"]
+
+    if args.impl == "reference":
+        run_reference_arm(args, wl, rank)
+        return 0
+
+    if args.gpus > 1 or world > 1:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "unit": UNIT, "n_gpus": args.gpus,
+                              "error": "row-slab multi-GPU path not built yet in this round; run with --gpus 1"}))
+        return 0
+
+    from equilibrium_b200 import _lib
+    lib = _lib.load()
+    if lib.eq_device_count() < 1:
+        raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
+
+    warmup = max(3, args.warmup)
+    steps = max(1, args.steps)
+    peak, peak_src = measured_peak_gbs()
+
+    # ---- exact mode, device-resident (the headline `value`) --------------------------
+    f = build_fluid(wl, "exact")
+    clocks = ClockSampler(0)
+    clocks.start()
+    ms = time_device_resident(f, n, steps, warmup, seed=0)
+    clk = clocks.stop()
+    value = n * n * steps / (ms * 1e-3)
+
+    # ---- per-phase device times with CUDA events on the launching stream ------------
+    f.profile_reset()
+    f.profile_enable(True)
+    f.step_n(steps)
+    prof = f.profile()
+    f.profile_enable(False)
+    ls_bytes = 12.0 * prof["lin_solve_cell_iters"]          # R x, R x0, W x per cell-iteration
+    ls_s = prof["lin_solve_ms"] * 1e-3
+    achieved = ls_bytes / ls_s / 1e9 if ls_s > 0 else 0.0
+    launches_per_step = (prof["lin_solve_launches"] + prof["advect_launches"] + prof["project_launches"] +
+                         prof["boundary_launches"] + prof["other_launches"]) / max(1, prof["steps"])
+    roofline = {
+        "bound": "hbm", "kernel": "k_linsolve_exact (wavefront Gauss-Seidel, all K iterations per launch)",
+        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": ls_bytes / max(1, prof["lin_solve_launches"]),
+        "share_of_step": prof["lin_solve_ms"] / max(1e-9, sum(prof[x] for x in
+                         ["lin_solve_ms", "advect_ms", "project_ms", "boundary_ms", "other_ms"])),
+        "step_effective_frac": (algorithmic_bytes_per_cell(k) * value) / 1e9 / peak,
+        "phases_ms_per_step": {x: prof[x] / max(1, prof["steps"]) for x in
+                               ["lin_solve_ms", "advect_ms", "project_ms", "boundary_ms", "other_ms"]},
+    }
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl_name(wl), "size": n, "gs_iterations": k, "rectangles": wl["rects"],
+                   "mode": "exact (bit-identical to the reference's lexicographic Gauss-Seidel)",
+                   "cache": "inputs larger than L2 (6 fields x %.0f MiB)" % (n * n * 4 / 2**20)
+                            if n >= 4096 else "L2-resident working set; L2 flushed before the timed region",
+                   "parallelism": "1 GPU"},
+        "roofline": roofline, "clocks": clk, "gpu_launches": int(round(launches_per_step * steps)),
+    }
+
+    if not args.no_extras:
+        # ---- e2e: through the public Fluid API with HOST buffers ------------------------
+        # per step: upload the pub fields (density, velocities_x, velocities_y) from pinned
+        # host memory, step(), download them back -- the host-mirror drop-in of `pub` Vecs.
+        bufs = [pinned_array(lib, (n, n), np.float32) for _ in range(3)]
+        names = ["density", "velocities_x", "velocities_y"]
+        for (a, _), nm in zip(bufs, names):
+            f.download(nm, a)
+        f.sync()
+        e2e_steps = max(1, min(steps, 3))
+        for it in range(1 + e2e_steps):
+            if it == 1:
+                t0 = time.perf_counter()
+            for (a, _), nm in zip(bufs, names):
+                f.upload(nm, a)
+            f.step()
+            for (a, _), nm in zip(bufs, names):
+                f.download(nm, a)
+        f.sync()
+        e2e_s = time.perf_counter() - t0
+        line["e2e"] = {"value": n * n * e2e_steps / e2e_s, "unit": UNIT,
+                       "h2d_bytes_per_step": 3 * n * n * 4, "d2h_bytes_per_step": 3 * n * n * 4,
+                       "ms_per_step": 1e3 * e2e_s / e2e_steps,
+                       "what": "Fluid.upload(pub fields) + Fluid.step() + Fluid.download(pub fields), pinned host buffers, wall clock"}
+        for _, p in bufs:
+            lib.eq_host_free(p)
+        f.close()
+
+        # ---- red-black fast path on the same workload -----------------------------------
+        g = build_fluid(wl, "red_black")
+        ms_rb = time_device_resident(g, n, steps, warmup, seed=0)
+        line["red_black"] = {"value": n * n * steps / (ms_rb * 1e-3), "unit": UNIT, "ms_per_step": ms_rb / steps,
+                             "note": "same K, red-black ordering; tolerance-checked, not bit-exact"}
+        g.close()
+
+        # ---- CPU baseline beside it -----------------------------------------------------
+        line["cpu_baseline"] = cpu_baseline(wl, 1)
+    else:
+        f.close()
+
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

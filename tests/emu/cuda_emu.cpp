@@ -16,7 +16,11 @@ static void run_block_threads(BlockState &bs, dim3 grid, dim3 block, uint3_emu b
                               const std::function<void()> &body, std::vector<std::thread> &pool) {
     const int nthreads = (int)(block.x * block.y * block.z);
     for (int t = 0; t < nthreads; ++t) {
-        pool.emplace_back([&, t, bid]() {
+        BlockState *bsp = &bs;
+        const std::function<void()> *bodyp = &body;
+        pool.emplace_back([bsp, bodyp, grid, block, t, bid]() {
+            BlockState &bs = *bsp;
+            const std::function<void()> &body = *bodyp;
             Ctx &c = ctx;
             c.tid = uint3_emu{(unsigned)t % block.x, ((unsigned)t / block.x) % block.y, (unsigned)t / (block.x * block.y)};
             c.bid = bid;

@@ -1,0 +1,82 @@
+"""Regenerates tests/golden/default_scene.json and default_scene_density_f16.npy.
+
+The reference is Rust and cannot be built or imported in the build image, and
+its own tests pin no output of step(), so these vectors come from
+the repo's CPU oracle (oracle/fluid_ref.c) AFTER the second, independently
+written restatement (oracle/pyref.py) reproduced every hashed state bit for bit.
+They pin the oracle against silent drift; they are not reference outputs.
+
+    python tests/golden/make_golden.py
+"""
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+sys.path.insert(0, os.path.dirname(HERE))
+
+from oracle import loader as O   # noqa: E402
+from oracle import pyref as P    # noqa: E402
+from parity import impulses      # noqa: E402
+
+FIELDS = [("density", 0, "density"), ("velocities_x", 1, "velocities_x"), ("velocities_y", 2, "velocities_y"),
+          ("velocities_x0", 3, "velocities_x0"), ("velocities_y0", 4, "velocities_y0"),
+          ("scratch_space", 5, "scratch_space")]
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def run(n, k, frames, rects, imp, checkpoints):
+    c = O.RefFluid(n, 0.02, k)
+    p = P.PyFluid(n, 0.02, k)
+    for r in rects:
+        c.fill_rect(*r)
+        p.fill_rect(*r)
+    out = {}
+    for fr in range(frames):
+        if imp:
+            _, x, y, ax, ay = imp[fr]
+            c.add_velocity(x, y, ax, ay)
+            p.add_velocity(x, y, ax, ay)
+        c.step()
+        p.step()
+        if fr + 1 in checkpoints:
+            rec = {}
+            for name, fid, pname in FIELDS:
+                a = c.field(fid)
+                b = getattr(p, pname).reshape(n, n)
+                assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (name, fr)
+                rec[name] = sha(a)
+            rec["density_sum"] = float(np.sum(c.density, dtype=np.float64))
+            rec["vx_absmax"] = float(np.abs(c.vx).max())
+            out[str(fr + 1)] = rec
+    return c, out
+
+
+def main():
+    gold = {"note": "oracle-generated (both restatements agree); not reference outputs",
+            "scenes": {}}
+    rect = [(80, 80, 110, 110)]                     # obstacle.rs:47-51
+    c, h = run(128, 16, 16, rect, None, {1, 4, 16})  # configs.rs:14-22 defaults, noise off
+    gold["scenes"]["default_128_k16"] = {"n": 128, "k": 16, "rects": rect, "impulse_seed": None,
+                                         "wall_cells": int(c.cells.sum()), "frames": h}
+    np.save(os.path.join(HERE, "default_scene_density_f16.npy"), c.density.copy())
+    c, h = run(128, 16, 8, rect, impulses(128, 8, seed=0), {2, 8})
+    gold["scenes"]["default_128_k16_impulses"] = {"n": 128, "k": 16, "rects": rect, "impulse_seed": 0,
+                                                  "wall_cells": int(c.cells.sum()), "frames": h}
+    c, h = run(64, 5, 6, [(10, 20, 30, 40), (40, 5, 50, 60)], impulses(64, 6, seed=3), {3, 6})
+    gold["scenes"]["small_64_k5_impulses"] = {"n": 64, "k": 5, "rects": [(10, 20, 30, 40), (40, 5, 50, 60)],
+                                              "impulse_seed": 3, "wall_cells": int(c.cells.sum()), "frames": h}
+    with open(os.path.join(HERE, "default_scene.json"), "w") as f:
+        json.dump(gold, f, indent=1, sort_keys=True)
+    print("written", os.path.join(HERE, "default_scene.json"))
+
+
+if __name__ == "__main__":
+    main()

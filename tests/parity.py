@@ -1,0 +1,141 @@
+"""Shared parity harness: drives the C ABI (real CUDA library or the emulated
+build of the same sources) and the CPU oracle on identical seeded inputs and
+compares bit patterns."""
+from __future__ import annotations
+
+import numpy as np
+
+from equilibrium_b200 import Fluid, FluidConfigs, Rectangle, SimulationConfigs
+
+ROW, COL, PASSIVE = 0, 1, 2
+ORIENT_NAMES = {ROW: "AdjustRow", COL: "AdjustColumn", PASSIVE: "Passive"}
+F32_FIELDS = [("density", 0), ("velocities_x", 1), ("velocities_y", 2),
+              ("velocities_x0", 3), ("velocities_y0", 4), ("scratch_space", 5)]
+
+
+def random_rects(n: int, count: int, seed: int):
+    """x0,y0 ~ U[1, N-2-w], w,h ~ U[N/64, N/16] (at least 1), all valid."""
+    rng = np.random.default_rng(seed)
+    out = []
+    lo, hi = max(1, n // 64), max(2, n // 16)
+    for _ in range(count):
+        w, h = int(rng.integers(lo, hi + 1)), int(rng.integers(lo, hi + 1))
+        x0, y0 = int(rng.integers(1, n - 2 - w + 1)), int(rng.integers(1, n - 2 - h + 1))
+        out.append((x0, y0, x0 + w, y0 + h))
+    return out
+
+
+def bits_equal(a: np.ndarray, b: np.ndarray) -> bool:
+    return np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def describe_diff(a, b):
+    bad = np.argwhere(a.view(np.uint32) != b.view(np.uint32))
+    return f"{len(bad)} cells differ, first (row, col): {bad[:5].tolist()}"
+
+
+def make_pair(oracle, lib_path, n, k, rects=(), *, frames=None, diffusion=0.0, viscosity=0.001,
+              dt=0.02, mode="exact"):
+    """A device fluid and an oracle fluid in the same state (Fluid::new + rectangles)."""
+    frames = k if frames is None else frames
+    gs = 0 if frames == k else k
+    dev = Fluid(FluidConfigs(diffusion=diffusion, viscousity=viscosity),
+                SimulationConfigs(dt, frames, n), lib_path=lib_path, mode=mode, gs_iterations=gs)
+    ref = oracle.RefFluid(n, dt, frames, diffusion, viscosity, gs_iterations=gs)
+    for (x0, y0, x1, y1) in rects:
+        dev.fill_obstacle(Rectangle((x0, y0), (x1, y1), n))
+        ref.fill_rect(x0, y0, x1, y1)
+    return dev, ref
+
+
+def assert_state_equal(dev, ref, where=""):
+    assert np.array_equal(dev.download("cells_type"), ref.cells), f"{where}: cells_type differs"
+    for name, fid in F32_FIELDS:
+        a, b = dev.download(name), ref.field(fid)
+        assert bits_equal(a, b), f"{where}: {name}: {describe_diff(a, b)}"
+
+
+def rnd(rng, n, scale=1.0):
+    return (rng.standard_normal((n, n)) * scale).astype(np.float32)
+
+
+def check_set_boundaries(oracle, lib_path, n, rects, orient, seed=0):
+    rng = np.random.default_rng(seed)
+    dev, ref = make_pair(oracle, lib_path, n, 1, rects)
+    x = rnd(rng, n)
+    dev.upload("velocities_x", x)
+    dev.op_set_boundaries(orient, "velocities_x")
+    oracle.set_boundaries(orient, x, ref.cells)
+    got = dev.download("velocities_x")
+    assert bits_equal(got, x), f"set_boundaries {ORIENT_NAMES[orient]} N={n}: {describe_diff(got, x)}"
+
+
+def check_lin_solve(oracle, lib_path, n, k, rects, orient, a=0.37, seed=0):
+    rng = np.random.default_rng(seed)
+    dev, ref = make_pair(oracle, lib_path, n, k, rects)
+    x, x0 = rnd(rng, n), rnd(rng, n)
+    dev.upload("velocities_x", x)
+    dev.upload("velocities_x0", x0)
+    c = float(np.float32(1.0) + np.float32(4.0) * np.float32(a))
+    dev.op_lin_solve(orient, "velocities_x", "velocities_x0", a, c, k)
+    oracle.lin_solve(orient, x, x0, a, c, k, ref.cells)
+    got = dev.download("velocities_x")
+    assert bits_equal(got, x), f"lin_solve {ORIENT_NAMES[orient]} N={n} K={k}: {describe_diff(got, x)}"
+
+
+def check_project(oracle, lib_path, n, k, rects, seed=0):
+    rng = np.random.default_rng(seed)
+    dev, ref = make_pair(oracle, lib_path, n, k, rects)
+    names = ["velocities_x", "velocities_y", "velocities_x0", "velocities_y0"]
+    arrs = [rnd(rng, n) for _ in names]
+    for nm, a in zip(names, arrs):
+        dev.upload(nm, a)
+    dev.op_project(*names, k)
+    oracle.project(*arrs, k, ref.cells)
+    for nm, a in zip(names, arrs):
+        got = dev.download(nm)
+        assert bits_equal(got, a), f"project N={n} K={k} {nm}: {describe_diff(got, a)}"
+
+
+def check_advect(oracle, lib_path, n, rects, orient, vscale=3.0, seed=0):
+    rng = np.random.default_rng(seed)
+    dev, ref = make_pair(oracle, lib_path, n, 1, rects)
+    d, d0 = rnd(rng, n), rnd(rng, n)
+    vx, vy = rnd(rng, n, vscale), rnd(rng, n, vscale)
+    for nm, a in zip(["density", "scratch_space", "velocities_x", "velocities_y"], [d, d0, vx, vy]):
+        dev.upload(nm, a)
+    dev.op_advect(orient, "density", "scratch_space", "velocities_x", "velocities_y")
+    oracle.advect(orient, d, d0, vx, vy, 0.02, ref.cells)
+    got = dev.download("density")
+    assert bits_equal(got, d), f"advect {ORIENT_NAMES[orient]} N={n}: {describe_diff(got, d)}"
+
+
+def impulses(n, frames, seed=0):
+    """scripted stand-in for add_noise: (N/2, N/2, U(-2N,2N), U(-2N,2N)) per frame."""
+    rng = np.random.default_rng(seed)
+    return [(fr, n // 2, n // 2, float(np.float32(rng.uniform(-2 * n, 2 * n))),
+             float(np.float32(rng.uniform(-2 * n, 2 * n)))) for fr in range(frames)]
+
+
+def check_steps(oracle, lib_path, n, k, frames_to_run, rects, *, with_impulses, diffusion=0.0,
+                every_frame=True, use_step_n=False, seed=0):
+    dev, ref = make_pair(oracle, lib_path, n, k, rects, diffusion=diffusion)
+    imp = impulses(n, frames_to_run, seed) if with_impulses else []
+    if use_step_n:
+        dev.step_n(frames_to_run, imp)
+        for (fr, x, y, ax, ay) in imp or [(f, 0, 0, 0, 0) for f in range(frames_to_run)]:
+            if imp:
+                ref.add_velocity(x, y, ax, ay)
+            ref.step()
+        assert_state_equal(dev, ref, f"N={n} K={k} after step_n({frames_to_run})")
+        return dev, ref
+    for fr in range(frames_to_run):
+        if imp:
+            _, x, y, ax, ay = imp[fr]
+            dev.add_velocity(x, y, ax, ay)
+            ref.add_velocity(x, y, ax, ay)
+        dev.step()
+        ref.step()
+        if every_frame or fr == frames_to_run - 1:
+            assert_state_equal(dev, ref, f"N={n} K={k} frame {fr}")
+    return dev, ref

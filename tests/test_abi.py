@@ -1,0 +1,66 @@
+"""CPU-only: the C-ABI library loads and exports every symbol include/*.h declares,
+the Python mirror declares a prototype for each, and host-side validation behaves
+like the reference.  No compute entry point is called (no GPU here)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from equilibrium_b200 import Rectangle, SimulationConfigs, FluidConfigs, _lib
+from conftest import CUDA_LIB, ROOT
+
+HEADER = os.path.join(ROOT, "include", "equilibrium_cuda.h")
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(eq_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_what_python_binds():
+    assert declared_symbols() == sorted(_lib.SIGNATURES)
+
+
+def test_library_exports_every_declared_symbol():
+    if not os.path.exists(CUDA_LIB):
+        from equilibrium_b200 import build
+        build.build()
+    lib = C.CDLL(CUDA_LIB)
+    for name in declared_symbols():
+        assert hasattr(lib, name), f"{name} missing from {CUDA_LIB}"
+    assert _lib.load(CUDA_LIB).eq_abi_version() == 1
+
+
+def test_struct_layout_matches_header():
+    assert C.sizeof(_lib.EqParams) == 4 + 4 + 8 + 8 + 4 + 4 + 4 + 4 + 4 + 4 + 128
+    assert C.sizeof(_lib.EqSource) == 8 + 4 + 4 + 4 + 4 + 4 + 4   # padded to 8
+    assert C.sizeof(_lib.EqProfile) == 12 * 8
+
+
+def test_rect_valid_needs_no_device():
+    lib = _lib.load(CUDA_LIB)
+    assert lib.eq_rect_valid(80, 80, 110, 110, 128) == 1
+    assert lib.eq_rect_valid(50, 120, 127, 110, 128) == 0      # obstacle.rs:100-107
+    assert lib.eq_rect_valid(12, 12, 10, 10, 128) == 0         # obstacle.rs:109-115
+
+
+def test_missing_library_fails_loudly(tmp_path):
+    with pytest.raises(ImportError):
+        _lib.load(str(tmp_path / "nope.so"))
+
+
+def test_rectangle_panics_like_the_reference():
+    with pytest.raises(ValueError):
+        Rectangle((50, 120), (127, 110), 128)
+    with pytest.raises(ValueError):
+        Rectangle((12, 12), (10, 10), 128)
+    r = Rectangle.default()
+    assert r.get_approximate_points() == [(80, 80), (110, 110)]
+
+
+def test_config_defaults_match_reference():
+    s, f = SimulationConfigs(), FluidConfigs()
+    assert (s.delta_t, s.frames, s.size) == (0.02, 16, 128)            # configs.rs:14-22
+    assert (f.diffusion, f.viscousity, f.has_perlin_noise) == (0.0, 0.001, True)   # configs.rs:50-60

@@ -1,0 +1,101 @@
+"""CPU-only: the PRODUCT kernel sources (equilibrium_b200/csrc) compiled against the
+host SIMT emulator in tests/emu and driven through the same C ABI, bit-compared
+with the oracle.  This checks kernel logic, the wavefront's ticket/flag protocol
+under real thread concurrency and the host-side composition of step() without a
+GPU; the -m gpu tests repeat the comparisons on the real device."""
+import numpy as np
+import pytest
+
+import parity as P
+
+RECTS64 = [(20, 30, 40, 45), (5, 5, 9, 60), (31, 1, 34, 33), (50, 50, 63, 63)]
+
+
+@pytest.mark.parametrize("orient", [P.ROW, P.COL, P.PASSIVE])
+def test_set_boundaries(oracle, emu_lib, orient):
+    P.check_set_boundaries(oracle, emu_lib, 64, RECTS64, orient)
+
+
+@pytest.mark.parametrize("orient", [P.ROW, P.COL, P.PASSIVE])
+@pytest.mark.parametrize("n,k,rects", [(64, 3, RECTS64), (45, 2, [(1, 1, 44, 2), (10, 3, 11, 44)]), (33, 1, [])])
+def test_lin_solve_exact(oracle, emu_lib, orient, n, k, rects):
+    P.check_lin_solve(oracle, emu_lib, n, k, rects, orient)
+
+
+def test_lin_solve_zero_iterations_is_a_no_op(oracle, emu_lib):
+    P.check_lin_solve(oracle, emu_lib, 32, 0, [], P.ROW)
+
+
+def test_project(oracle, emu_lib):
+    P.check_project(oracle, emu_lib, 64, 3, RECTS64)
+
+
+@pytest.mark.parametrize("orient", [P.ROW, P.COL, P.PASSIVE])
+def test_advect_with_row_break(oracle, emu_lib, orient):
+    P.check_advect(oracle, emu_lib, 48, [(10, 10, 20, 30)], orient, vscale=4.0)
+
+
+def test_full_steps_with_impulses(oracle, emu_lib):
+    P.check_steps(oracle, emu_lib, 64, 4, 3, [(20, 30, 40, 45)], with_impulses=True)
+
+
+def test_full_steps_ragged_size_and_diffusion(oracle, emu_lib):
+    P.check_steps(oracle, emu_lib, 50, 2, 2, [(10, 10, 20, 45), (30, 1, 31, 49)], with_impulses=True,
+                  diffusion=1e-3)
+
+
+def test_step_n_with_sources_and_clone(oracle, emu_lib):
+    dev, ref = P.check_steps(oracle, emu_lib, 40, 2, 3, [(5, 5, 15, 15)], with_impulses=True, use_step_n=True)
+    twin = dev.clone()
+    dev.step()
+    ref.step()
+    P.assert_state_equal(dev, ref, "after clone + step")
+    assert not P.bits_equal(twin.download("velocities_x"), dev.download("velocities_x"))
+
+
+def test_default_double_init_and_reset_walls(oracle, emu_lib):
+    from equilibrium_b200 import Fluid, Rectangle
+    dev = Fluid.default(lib_path=emu_lib)
+    ref = oracle.RefFluid(128, 0.02, 16)
+    ref.init()
+    P.assert_state_equal(dev, ref, "Fluid::default")
+    dev.fill_obstacle(Rectangle.default())
+    assert int(dev.cells_type.sum()) == 1408          # renderer_helpers.rs:222-252
+    dev.reset_walls()
+    assert int(dev.cells_type.sum()) == 2 * (128 + 126)
+
+
+def test_fill_obstacle_clamps_like_idx(oracle, emu_lib):
+    dev, ref = P.make_pair(oracle, emu_lib, 32, 1)
+    for r in [(-5, 10, 4, 12), (28, 28, 40, 40), (3, 3, 3, 9), (9, 9, 5, 12)]:
+        class R:
+            def get_approximate_points(self, r=r):
+                return [(r[0], r[1]), (r[2], r[3])]
+        dev.fill_obstacle(R())
+        ref.fill_rect(*r)
+    assert np.array_equal(dev.cells_type, ref.cells)
+
+
+def test_upload_rejects_open_frame(emu_lib):
+    from equilibrium_b200 import Fluid, FluidConfigs, SimulationConfigs, EquilibriumError
+    dev = Fluid(FluidConfigs(), SimulationConfigs(0.02, 1, 24), lib_path=emu_lib)
+    cells = dev.cells_type
+    cells[0, 5] = 0
+    with pytest.raises(EquilibriumError):
+        dev.upload("cells_type", cells)
+
+
+def test_red_black_close_to_oracle_red_black(oracle, emu_lib):
+    # the fast path is checked against the red-black restatement bitwise and against the
+    # lexicographic oracle within tolerance (tests/test_red_black.py does the latter on GPU)
+    rng = np.random.default_rng(0)
+    n, k = 48, 6
+    dev, ref = P.make_pair(oracle, emu_lib, n, k, [(10, 10, 20, 30)], mode="red_black")
+    for orient in (P.ROW, P.COL, P.PASSIVE):
+        x, x0 = P.rnd(rng, n), P.rnd(rng, n)
+        dev.upload("velocities_x", x)
+        dev.upload("velocities_x0", x0)
+        dev.op_lin_solve(orient, "velocities_x", "velocities_x0", 0.37, 2.48, k)
+        oracle.lin_solve(orient, x, x0, 0.37, 2.48, k, ref.cells, red_black=True)
+        got = dev.download("velocities_x")
+        assert P.bits_equal(got, x), P.describe_diff(got, x)
