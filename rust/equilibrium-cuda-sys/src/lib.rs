@@ -1,0 +1,68 @@
+//! Raw bindings to `include/equilibrium_cuda.h` (ABI version 1).
+#![allow(non_camel_case_types)]
+use std::os::raw::{c_char, c_int, c_void};
+
+#[repr(C)]
+pub struct eq_fluid {
+    _private: [u8; 0],
+}
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct EqParams {
+    pub size: u32,
+    pub delta_t: f32,
+    pub frames: i64,
+    pub gs_iterations: i64,
+    pub diffusion: f32,
+    pub viscosity: f32,
+    pub mode: i32,
+    pub device: i32,
+    pub rank: i32,
+    pub world: i32,
+    pub comm_id: [u8; 128],
+}
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct EqSource {
+    pub frame: i64,
+    pub x: u32,
+    pub y: u32,
+    pub d_vx: f32,
+    pub d_vy: f32,
+    pub d_density: f32,
+}
+
+pub const EQ_OK: c_int = 0;
+pub const EQ_MODE_EXACT: i32 = 0;
+pub const EQ_MODE_RED_BLACK: i32 = 1;
+pub const EQ_F_DENSITY: c_int = 0;
+pub const EQ_F_VX: c_int = 1;
+pub const EQ_F_VY: c_int = 2;
+pub const EQ_F_VX0: c_int = 3;
+pub const EQ_F_VY0: c_int = 4;
+pub const EQ_F_SCRATCH: c_int = 5;
+pub const EQ_F_CELLS: c_int = 6;
+
+extern "C" {
+    pub fn eq_last_error() -> *const c_char;
+    pub fn eq_abi_version() -> c_int;
+    pub fn eq_device_count() -> c_int;
+    pub fn eq_create(params: *const EqParams, out: *mut *mut eq_fluid) -> c_int;
+    pub fn eq_destroy(h: *mut eq_fluid) -> c_int;
+    pub fn eq_clone(h: *mut eq_fluid, out: *mut *mut eq_fluid) -> c_int;
+    pub fn eq_init_default(h: *mut eq_fluid) -> c_int;
+    pub fn eq_add_density(h: *mut eq_fluid, x: u32, y: u32, amount: f32) -> c_int;
+    pub fn eq_add_velocity(h: *mut eq_fluid, x: u32, y: u32, ax: f32, ay: f32) -> c_int;
+    pub fn eq_rect_valid(x0: i64, y0: i64, x1: i64, y1: i64, size: i64) -> c_int;
+    pub fn eq_fill_rect(h: *mut eq_fluid, x0: i64, y0: i64, x1: i64, y1: i64) -> c_int;
+    pub fn eq_reset_walls(h: *mut eq_fluid) -> c_int;
+    pub fn eq_set_params(h: *mut eq_fluid, params: *const EqParams) -> c_int;
+    pub fn eq_get_params(h: *mut eq_fluid, out: *mut EqParams) -> c_int;
+    pub fn eq_step(h: *mut eq_fluid) -> c_int;
+    pub fn eq_step_n(h: *mut eq_fluid, n: i64, sources: *const EqSource, n_sources: i64) -> c_int;
+    pub fn eq_sync(h: *mut eq_fluid) -> c_int;
+    pub fn eq_upload(h: *mut eq_fluid, field: c_int, host: *const c_void, bytes: usize) -> c_int;
+    pub fn eq_download(h: *mut eq_fluid, field: c_int, host: *mut c_void, bytes: usize) -> c_int;
+}
