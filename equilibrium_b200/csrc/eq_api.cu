@@ -71,7 +71,7 @@ struct eq_fluid {
     float *f[6];            // EQ_F_DENSITY .. EQ_F_SCRATCH
     uint8_t *cells;
     // mask-derived tables (rebuilt lazily when the mask changed)
-    uint8_t *codes, *row_fluid, *col_fluid;
+    uint8_t *codes, *row_fluid, *col_fluid, *chunk_flags;
     unsigned *counts;       // [4] device
     uint2 *row_list, *col_list;
     unsigned n_row, n_col;
@@ -164,8 +164,9 @@ static int ensure_tables(eq_fluid *h) {
     CU(cudaMemsetAsync(h->counts, 0, 4 * sizeof(unsigned), h->stream));
     CU(cudaMemsetAsync(h->row_fluid, 0, L.N, h->stream));
     CU(cudaMemsetAsync(h->col_fluid, 0, L.N, h->stream));
+    CU(cudaMemsetAsync(h->chunk_flags, 0, 2 * (size_t)((L.N - 2 + 31) / 32) * ((L.N + 31) / 32), h->stream));
     EQ_LAUNCH(k_build_codes, row_grid(h, L.N), 256, 0, h->stream, h->cells, h->codes, h->row_fluid, h->col_fluid,
-                                                           h->counts, nullptr, nullptr, 0, L);
+              h->chunk_flags, h->counts, nullptr, nullptr, 0, L);
     TRY(check_launch("k_build_codes"));
     unsigned counts[4];
     CU(cudaMemcpyAsync(counts, h->counts, sizeof(counts), cudaMemcpyDeviceToHost, h->stream));
@@ -183,7 +184,7 @@ static int ensure_tables(eq_fluid *h) {
         CU(cudaMalloc(&h->col_list, h->cap_col * sizeof(uint2)));
     }
     EQ_LAUNCH(k_build_codes, row_grid(h, L.N), 256, 0, h->stream, h->cells, h->codes, h->row_fluid, h->col_fluid,
-                                                           h->counts, h->row_list, h->col_list, 1, L);
+              h->chunk_flags, h->counts, h->row_list, h->col_list, 1, L);
     TRY(check_launch("k_build_codes(lists)"));
     h->n_row = counts[0];
     h->n_col = counts[1];
@@ -268,6 +269,7 @@ static int lin_solve_exact(eq_fluid *h, const LinSolveReq *req, int nreq, int64_
             p.prob[i].orient = req[i].orient;
         }
         p.codes = h->codes;
+        p.chunk_flags = h->chunk_flags;
         p.row_fluid = h->row_fluid;
         p.col_fluid = h->col_fluid;
         p.jobs = jobs;
@@ -283,7 +285,7 @@ static int lin_solve_exact(eq_fluid *h, const LinSolveReq *req, int nreq, int64_
         CU(cudaMemsetAsync(h->flags, 0, sizeof(unsigned), h->stream));
         CU(cudaMemsetAsync(h->flags + 8, 0, (size_t)nreq * prog_words * sizeof(unsigned), h->stream));
         const int grid = std::min(h->lsx_ctas, p.njobs * nreq);
-        EQ_LAUNCH(k_linsolve_exact, grid, 32, sizeof(LsxSmem), h->stream, p);
+        EQ_LAUNCH(k_linsolve_exact, grid, 32, LSX_SMEM_BYTES, h->stream, p);
         TRY(check_launch("k_linsolve_exact"));
         done += kc;
     }
@@ -458,6 +460,7 @@ static int alloc_handle(const EqParams *params, eq_fluid **out) {
     CU(cudaMalloc(&h->row_fluid, h->L.N));
     CU(cudaMalloc(&h->col_fluid, h->L.N));
     CU(cudaMalloc(&h->counts, 4 * sizeof(unsigned)));
+    CU(cudaMalloc(&h->chunk_flags, 2 * (size_t)((h->L.N - 2 + 31) / 32) * ((h->L.N + 31) / 32)));
     const int NB = (h->L.N - 2 + 31) / 32;
     for (int i = 0; i < 2; ++i) {
         CU(cudaMalloc(&h->raw[i], (size_t)NB * h->L.P * sizeof(float)));
@@ -466,9 +469,9 @@ static int alloc_handle(const EqParams *params, eq_fluid **out) {
     h->flags_words = 8 + 2 * (size_t)LSX_KMAX * NB;
     CU(cudaMalloc(&h->flags, h->flags_words * sizeof(unsigned)));
     CU(cudaMemsetAsync(h->flags, 0, h->flags_words * sizeof(unsigned), h->stream));
-    CU(cudaFuncSetAttribute(k_linsolve_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LsxSmem)));
+    CU(cudaFuncSetAttribute(k_linsolve_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LSX_SMEM_BYTES));
     int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_linsolve_exact, 32, sizeof(LsxSmem)));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_linsolve_exact, 32, LSX_SMEM_BYTES));
     h->lsx_ctas = std::max(1, per_sm) * h->sm_count;
     return EQ_OK;
 }
@@ -536,6 +539,7 @@ int eq_destroy(eq_fluid *h) {
     cudaFree(h->row_fluid);
     cudaFree(h->col_fluid);
     cudaFree(h->counts);
+    cudaFree(h->chunk_flags);
     cudaFree(h->row_list);
     cudaFree(h->col_list);
     cudaFree(h->raw[0]);

@@ -10,12 +10,13 @@
 //
 // Decomposition (DESIGN.md "Exact lin_solve"):
 //   job (b,k)  = rows j0..j0+31 (j0 = 1+32b) of iteration k, run by ONE warp,
-//                lane r = row j0+r, lane r trails lane r-1 by one column, so the
-//                warp walks an anti-diagonal along the row; R_k(i,j-1) arrives by
-//                __shfl_up, R_k(i-1,j) is the lane's own previous result.
+//                lane r = row j0+r, lane r trails lane r-1 by one column (at step s
+//                lane r computes column s-r), so the warp walks an anti-diagonal
+//                along the row; R_k(i,j-1) arrives by __shfl_up, R_k(i-1,j) is the
+//                lane's own previous result.
 //   job (b,k) needs (b-1,k)   : R_k of row j0-1 (a "raw" side stream, because
 //                               global x only ever holds fixed values), and
-//             and (b+1,k-1)   : F_{k-1} of rows j0..j0+32.
+//                   (b+1,k-1) : F_{k-1} of rows j0..j0+32.
 //   Jobs are handed out by an atomic ticket in wavefront order w = b + 2k, so a
 //   job only ever waits for lower tickets (already running or done): no
 //   co-residency requirement, no deadlock.  Progress is published per 32-column
@@ -25,14 +26,33 @@
 //   in registers, the down source comes by __shfl_down; across a band edge the
 //   lower band patches the one cell above it).
 //
-// HBM traffic per cell-iteration: read x, x0, write x (12 B) + 1 B code in the
-// AdjustRow/AdjustColumn orientations + 8/32 B for the raw stream.
+// Shared memory per warp (38 272 B): a 4-chunk ring (128 columns) of
+//   x   rows j0-1 .. j0+32   (34 x 512 B)     addr = tr*512 + (c & 127)*4
+//   x0  rows j0   .. j0+31   (32 x 512 B)
+//   fix-up codes rows j0-1 .. j0+31 (33 x 128 B)
+// A lane reads column c of its own row while its neighbours read c+1 / c-1: the
+// row pitch is a multiple of 32 banks, so the diagonal access is conflict-free.
+// All shared accesses use explicit 32-bit shared addresses (no generic->shared
+// conversion in the loop).
+//
+// Macro step m = steps 32m..32m+31 touches chunks m-1, m, m+1.  When every lane is
+// on an interior column and the (band, chunk) summary says no cell of those chunks
+// has a fix-up code, the macro step runs a branch-free fast loop (3 LDS, 1 SHFL,
+// 6 FP ops, 1 STS per step); otherwise a general loop handles frame columns,
+// fix-ups and the Passive frame copies.
+//
+// HBM traffic per cell-iteration: read x, x0, write x (12 B) + 1 B code only for
+// chunks that contain fix-ups + 8/32 B for the raw stream.
 #pragma once
 #include "eq_common.cuh"
 
-#define LSX_SLOTS 4
 #define LSX_XROWS 34   // rows j0-1 .. j0+32
 #define LSX_CROWS 33   // code rows j0-1 .. j0+31
+#define LSX_XS_OFF 0u
+#define LSX_X0_OFF (LSX_XROWS * 512u)
+#define LSX_CS_OFF (LSX_X0_OFF + 32u * 512u)
+#define LSX_RAW_OFF (LSX_CS_OFF + LSX_CROWS * 128u)
+#define LSX_SMEM_BYTES (LSX_RAW_OFF + 64u * 4u)
 #define LSX_SPIN_LIMIT (1u << 22)
 
 struct LsxProblem {
@@ -47,40 +67,46 @@ struct LsxProblem {
 struct LsxParams {
     LsxProblem prob[2];
     int nprob;
-    const uint8_t *codes;      // per-cell fix-up codes, pitch P
-    const uint8_t *row_fluid;  // [N] row j has a NoWall cell   (quirk Q6)
-    const uint8_t *col_fluid;  // [N] column i has a NoWall cell
-    const uint32_t *jobs;      // [K*NB] (k << 16 | b) in wavefront order
-    int njobs;                 // K*NB (per problem)
+    const uint8_t *codes;        // per-cell fix-up codes, pitch P
+    const uint8_t *chunk_flags;  // [2][NB][NC]: (band, chunk) holds an AdjustRow ([0]) / AdjustColumn ([1]) code
+    const uint8_t *row_fluid;    // [N] row j has a NoWall cell   (quirk Q6)
+    const uint8_t *col_fluid;    // [N] column i has a NoWall cell
+    const uint32_t *jobs;        // [K*NB] (k << 16 | b) in wavefront order
+    int njobs;                   // K*NB (per problem)
     int N, P, K, NB, NC;
     unsigned *ticket;
     int *error;
 };
 
-struct LsxSmem {
-    float xs[LSX_SLOTS][LSX_XROWS][32];
-    float x0s[LSX_SLOTS][32][32];
-    uint8_t cs[LSX_SLOTS][LSX_CROWS][32];
-    float rawbuf[64];
-};
-
-__device__ __forceinline__ bool lsx_wait_ge(const unsigned *flag, unsigned need, int *error) {
-    unsigned spins = 0;
-    while (ld_acquire_u32(flag) < need) {
-        __nanosleep(40);
-        if ((++spins & 1023u) == 0) {
-            if (spins >= LSX_SPIN_LIMIT) {
-                *error = 1;
-                return false;
+// lane 0 polls (relaxed), then one acq_rel fence turns the observation into an acquire for
+// the whole warp (the warp-level sync that follows orders the other lanes after it).
+__device__ __forceinline__ bool lsx_wait2(const unsigned *f1, unsigned n1, const unsigned *f2, unsigned n2,
+                                          int *error) {
+    int ok = 1;
+    if (threadIdx.x == 0) {
+        unsigned spins = 0;
+        while ((f1 && ld_relaxed_u32(f1) < n1) || (f2 && ld_relaxed_u32(f2) < n2)) {
+            __nanosleep(32);
+            if ((++spins & 1023u) == 0) {
+                if (spins >= LSX_SPIN_LIMIT) {
+                    *error = 1;
+                    ok = 0;
+                    break;
+                }
+                if (ld_volatile_s32(error) != 0) {
+                    ok = 0;
+                    break;
+                }
             }
-            if (ld_volatile_s32(error) != 0) return false;
         }
+        fence_acq_rel_gpu();
     }
-    return true;
+    ok = __shfl_sync(0xffffffffu, ok, 0);
+    return ok != 0;
 }
 
 template <int ORIENT>
-__device__ __forceinline__ bool lsx_run_job(const LsxParams &p, const LsxProblem &pr, LsxSmem &sm,
+__device__ __forceinline__ bool lsx_run_job(const LsxParams &p, const LsxProblem &pr, const uint32_t sbase,
                                             const int b, const int k) {
     const int lane = threadIdx.x;
     const int N = p.N, P = p.P, NC = p.NC, NB = p.NB;
@@ -89,6 +115,7 @@ __device__ __forceinline__ bool lsx_run_job(const LsxParams &p, const LsxProblem
     const int tr = lane + 1;
     const bool in_row = (j <= N - 2);
     const bool last_band = (b == NB - 1);
+    const bool full_band = (j0 + 31 <= N - 2);
     const float a = pr.a, c_recip = pr.c_recip;
     float *__restrict__ x = pr.x;
     const float *__restrict__ x0 = pr.x0;
@@ -98,12 +125,31 @@ __device__ __forceinline__ bool lsx_run_job(const LsxParams &p, const LsxProblem
     const float *top_src = (b > 0) ? pr.raw + (size_t)b * P : x;  // row j0-1: raw stream or frame row 0
     float *raw_out = (b + 1 < NB) ? pr.raw + (size_t)(b + 1) * P : nullptr;
     const bool row_has_fluid = (ORIENT == EQ_PASSIVE && in_row) ? (p.row_fluid[j] != 0) : false;
+    const uint8_t *cflags = p.chunk_flags + (ORIENT == EQ_ADJUST_COLUMN ? (size_t)NB * NC : 0) + (size_t)b * NC;
+
+    // shared addresses of this lane's rows
+    const uint32_t xs_row = sbase + LSX_XS_OFF + (uint32_t)tr * 512u;     // own row
+    const uint32_t xs_top = sbase + LSX_XS_OFF;                            // row j0-1
+    const uint32_t x0_row = sbase + LSX_X0_OFF + (uint32_t)lane * 512u;
+    const uint32_t cs_row = sbase + LSX_CS_OFF + (uint32_t)tr * 128u;
+    const uint32_t cs_top = sbase + LSX_CS_OFF;
+    const uint32_t raw_s = sbase + LSX_RAW_OFF;
+
+    // macro step m can take the fast loop iff every lane stays on interior columns with an
+    // interior column to finalise, the band is full, no Passive frame row is involved and
+    // chunks m-1, m carry no fix-up code of this orientation.
+    const int S = N + 31;                    // steps 0 .. N+30
+    const int M = (S + 31) >> 5;
+    auto fast_ok = [&](int m) -> bool {
+        if (m < 2 || 32 * m + 31 > N - 2 || !full_band) return false;
+        if (ORIENT == EQ_PASSIVE) return b != 0 && !last_band;
+        return (cflags[m - 1] | cflags[m]) == 0;
+    };
 
     auto load_chunk = [&](int q) -> bool {
         if (q < NC) {
-            if (flag_prev_iter && !lsx_wait_ge(flag_prev_iter, (unsigned)q + 1u, p.error)) return false;
-            if (flag_band_above && !lsx_wait_ge(flag_band_above, (unsigned)q + 1u, p.error)) return false;
-            const int slot = q & (LSX_SLOTS - 1);
+            if (!lsx_wait2(flag_prev_iter, (unsigned)q + 1u, flag_band_above, (unsigned)q + 1u, p.error)) return false;
+            const uint32_t slot = (uint32_t)(q & 3) * 128u;   // byte offset of the chunk inside a 512 B row
             const int col0 = 32 * q;
             {   // x rows j0-1 .. j0+32 : 8 lanes x 16 B per row, 4 rows per pass
                 const int sub = lane & 7, rr = lane >> 3;
@@ -113,22 +159,26 @@ __device__ __forceinline__ bool lsx_run_job(const LsxParams &p, const LsxProblem
                     if (t < LSX_XROWS) {
                         const float *src = (t == 0) ? top_src + col0 + 4 * sub
                                                     : x + (size_t)(j0 - 1 + t) * P + col0 + 4 * sub;
-                        cp_async_16(&sm.xs[slot][t][4 * sub], src);
+                        cp_async_16s(sbase + LSX_XS_OFF + (uint32_t)t * 512u + slot + 16u * sub, src);
                     }
                 }
 #pragma unroll
                 for (int g = 0; g < 8; ++g) {
                     const int t = 4 * g + rr;
-                    cp_async_16(&sm.x0s[slot][t][4 * sub], x0 + (size_t)(j0 + t) * P + col0 + 4 * sub);
+                    cp_async_16s(sbase + LSX_X0_OFF + (uint32_t)t * 512u + slot + 16u * sub,
+                                 x0 + (size_t)(j0 + t) * P + col0 + 4 * sub);
                 }
             }
-            if (ORIENT != EQ_PASSIVE) {   // codes rows j0-1 .. j0+31 : 2 lanes x 16 B per row
+            // codes rows j0-1 .. j0+31 (2 lanes x 16 B per row), skipped when both macro steps
+            // that touch this chunk take the fast loop
+            if (ORIENT != EQ_PASSIVE && !(fast_ok(q) && fast_ok(q + 1))) {
                 const int sub = lane & 1, rr = lane >> 1;
 #pragma unroll
                 for (int g = 0; g < 3; ++g) {
                     const int t = 16 * g + rr;
                     if (t < LSX_CROWS)
-                        cp_async_16(&sm.cs[slot][t][16 * sub], p.codes + (size_t)(j0 - 1 + t) * P + col0 + 16 * sub);
+                        cp_async_16s(sbase + LSX_CS_OFF + (uint32_t)t * 128u + (uint32_t)(q & 3) * 32u + 16u * sub,
+                                     p.codes + (size_t)(j0 - 1 + t) * P + col0 + 16 * sub);
                 }
             }
         }
@@ -137,7 +187,7 @@ __device__ __forceinline__ bool lsx_run_job(const LsxParams &p, const LsxProblem
     };
 
     auto store_chunk = [&](int q) {
-        const int slot = q & (LSX_SLOTS - 1);
+        const uint32_t slot = (uint32_t)(q & 3) * 128u;
         const int col0 = 32 * q;
         const int sub = lane & 7, rr = lane >> 3;
         // band rows (tile rows 1..32); the bottom frame row N-1 travels with the last band
@@ -148,28 +198,23 @@ __device__ __forceinline__ bool lsx_run_job(const LsxParams &p, const LsxProblem
             const int t = 4 * g + rr;
             const int row = j0 - 1 + t;
             if (t >= t_lo && t <= t_hi && row <= N - 1) {
-                const float4 v = *reinterpret_cast<const float4 *>(&sm.xs[slot][t][4 * sub]);
+                const float4 v = lds_f32x4(sbase + LSX_XS_OFF + (uint32_t)t * 512u + slot + 16u * sub);
                 *reinterpret_cast<float4 *>(x + (size_t)row * P + col0 + 4 * sub) = v;
             }
         }
-        if (raw_out) raw_out[col0 + lane] = sm.rawbuf[(col0 + lane) & 63];
+        if (raw_out) raw_out[col0 + lane] = lds_f32(raw_s + (uint32_t)((col0 + lane) & 63) * 4u);
     };
 
     auto publish = [&](unsigned chunks_done) {
-        __threadfence();
-        __syncwarp();
-        if (lane == 0) st_release_u32(my_flag, chunks_done);
+        __syncwarp();                                  // every lane's stores are ordered before lane 0 ...
+        if (lane == 0) st_release_u32(my_flag, chunks_done);   // ... whose release makes them visible GPU-wide
     };
-
-#define XS(t, col) sm.xs[((col) >> 5) & (LSX_SLOTS - 1)][(t)][(col) & 31]
 
     // prologue: chunks 0 and 1
     if (!load_chunk(0)) return false;
     if (!load_chunk(1)) return false;
 
     float cur = 0.f, prev2 = 0.f, prev_up = 0.f;
-    const int S = N + 31;                    // steps 0 .. N+30 (lane r computes column s-r)
-    const int M = (S + 31) >> 5;
     int stored = 0;                          // chunks stored so far
 
     for (int m = 0; m < M; ++m) {
@@ -177,67 +222,92 @@ __device__ __forceinline__ bool lsx_run_job(const LsxParams &p, const LsxProblem
         cp_async_wait<1>();                  // chunk m+1 (and older) has landed
         __syncwarp();
 
-        const int s_end = min(32 * m + 32, S);
-        for (int s = 32 * m; s < s_end; ++s) {
-            const int c = s - lane;          // column this lane computes now (0 = left frame cell)
-            const float up = __shfl_up_sync(0xffffffffu, cur, 1);
-            float newv = cur;
-            float top = up;
-            if (c >= 0 && c <= N - 1) {
+        if (fast_ok(m)) {
+            // ---- fast loop: all lanes interior, no fix-ups ------------------------------------
+            uint32_t o = ((uint32_t)(32 * m - lane) & 127u) << 2;      // byte offset of column c
+            uint32_t om1 = (o - 4u) & 508u;                            // column c-1
+#pragma unroll 4
+            for (int t = 0; t < 32; ++t) {
+                const uint32_t o1 = (o + 4u) & 508u;
+                float up = __shfl_up_sync(0xffffffffu, cur, 1);
+                const float right = lds_f32(xs_row + o1);
+                const float down = lds_f32(xs_row + 512u + o);
+                const float x0v = lds_f32(x0_row + o);
+                if (lane == 0) up = lds_f32(xs_top + o);
+                const float newv = gs_update(x0v, right, cur, down, up, a, c_recip);
+                sts_f32(xs_row + om1, cur);                            // column c-1 is final: F = R
+                if (lane == 31) sts_f32(raw_s + (o & 252u), newv);
+                prev2 = cur;
+                prev_up = up;
+                cur = newv;
+                om1 = o;
+                o = o1;
+                __syncwarp();
+            }
+        } else {
+            // ---- general loop: frame columns, fix-ups, Passive frame copies ----------------------
+            const int s_end = min(32 * m + 32, S);
+            for (int s = 32 * m; s < s_end; ++s) {
+                const int c = s - lane;          // column this lane computes now (0 = left frame cell)
+                const uint32_t o = ((uint32_t)c & 127u) << 2;
+                const uint32_t om1 = (o - 4u) & 508u;
+                const float up = __shfl_up_sync(0xffffffffu, cur, 1);
+                float newv = cur;
+                float top = up;
+                if (c >= 0 && c <= N - 1) {
+                    if (in_row && c >= 1 && c <= N - 2) {
+                        const float right = lds_f32(xs_row + ((o + 4u) & 508u));
+                        const float down = lds_f32(xs_row + 512u + o);
+                        if (lane == 0) top = lds_f32(xs_top + o);
+                        const float x0v = lds_f32(x0_row + o);
+                        newv = gs_update(x0v, right, cur, down, top, a, c_recip);
+                    } else if (in_row || ORIENT == EQ_ADJUST_COLUMN) {
+                        newv = lds_f32(xs_row + o);      // frame column / frame row N-1: pass through
+                    }
+                }
+                float dn = 0.f;
+                if (ORIENT == EQ_ADJUST_COLUMN) dn = __shfl_down_sync(0xffffffffu, newv, 1);
+                const int cf = c - 1;            // column finalised now
+                if (in_row && cf >= 1 && cf <= N - 2) {
+                    float F = cur;               // R_k(cf, j)
+                    if (ORIENT == EQ_ADJUST_ROW) {
+                        const unsigned code = lds_u8(cs_row + (om1 >> 2)) & 3u;
+                        if (code == EQ_CODE_ROW_RIGHT) F = -newv;
+                        else if (code == EQ_CODE_ROW_LEFT) F = -prev2;
+                    } else if (ORIENT == EQ_ADJUST_COLUMN) {
+                        const unsigned code = lds_u8(cs_row + (om1 >> 2)) & 12u;
+                        if (code == EQ_CODE_COL_UP) F = -prev_up;
+                        else if (code == EQ_CODE_COL_DOWN) {
+                            if (lane < 31) F = -dn;
+                            else if (last_band) F = -lds_f32(xs_top + 33u * 512u + om1);
+                            // else: the band below patches this cell (see below)
+                        }
+                    }
+                    sts_f32(xs_row + om1, F);
+                    if (ORIENT == EQ_PASSIVE) {   // fluid.rs:179-187, conditional per quirk Q6
+                        if (row_has_fluid) {
+                            if (cf == 1) sts_f32(xs_row, cur);
+                            if (cf == N - 2) sts_f32(xs_row + (((uint32_t)(N - 1) & 127u) << 2), cur);
+                        }
+                        if ((j == 1 || j == N - 2) && p.col_fluid[cf]) {
+                            if (j == 1) sts_f32(xs_top + om1, cur);
+                            if (j == N - 2) sts_f32(xs_row + 512u + om1, cur);
+                        }
+                    }
+                }
                 if (in_row && c >= 1 && c <= N - 2) {
-                    const float right = XS(tr, c + 1);
-                    const float down = XS(tr + 1, c);
-                    if (lane == 0) top = XS(0, c);
-                    const float x0v = sm.x0s[(c >> 5) & (LSX_SLOTS - 1)][lane][c & 31];
-                    newv = gs_update(x0v, right, cur, down, top, a, c_recip);
-                } else if (in_row || ORIENT == EQ_ADJUST_COLUMN) {
-                    newv = XS(tr, c);        // frame column / frame row N-1: pass through
-                }
-            }
-            float dn = 0.f;
-            if (ORIENT == EQ_ADJUST_COLUMN) {
-                dn = __shfl_down_sync(0xffffffffu, newv, 1);
-            }
-            const int cf = c - 1;            // column finalised now
-            if (in_row && cf >= 1 && cf <= N - 2) {
-                float F = cur;               // R_k(cf, j)
-                if (ORIENT == EQ_ADJUST_ROW) {
-                    const unsigned code = sm.cs[(cf >> 5) & (LSX_SLOTS - 1)][tr][cf & 31] & 3u;
-                    if (code == EQ_CODE_ROW_RIGHT) F = -newv;
-                    else if (code == EQ_CODE_ROW_LEFT) F = -prev2;
-                } else if (ORIENT == EQ_ADJUST_COLUMN) {
-                    const unsigned code = sm.cs[(cf >> 5) & (LSX_SLOTS - 1)][tr][cf & 31] & 12u;
-                    if (code == EQ_CODE_COL_UP) F = -prev_up;
-                    else if (code == EQ_CODE_COL_DOWN) {
-                        if (lane < 31) F = -dn;
-                        else if (last_band) F = -XS(33, cf);
-                        // else: the band below patches this cell (see below)
+                    if (ORIENT == EQ_ADJUST_COLUMN && lane == 0 && b > 0) {
+                        // cell (c, j0-1) of the band above takes -R_k(c, j0) when its code says DOWN
+                        const unsigned code0 = lds_u8(cs_top + (o >> 2)) & 12u;
+                        if (code0 == EQ_CODE_COL_DOWN) x[(size_t)(j0 - 1) * P + c] = -newv;
                     }
+                    if (lane == 31) sts_f32(raw_s + (o & 252u), newv);
                 }
-                XS(tr, cf) = F;
-                if (ORIENT == EQ_PASSIVE) {   // fluid.rs:179-187, conditional per quirk Q6
-                    if (row_has_fluid) {
-                        if (cf == 1) XS(tr, 0) = cur;
-                        if (cf == N - 2) XS(tr, N - 1) = cur;
-                    }
-                    if ((j == 1 || j == N - 2) && p.col_fluid[cf]) {
-                        if (j == 1) XS(0, cf) = cur;
-                        if (j == N - 2) XS(tr + 1, cf) = cur;
-                    }
-                }
+                prev2 = cur;
+                prev_up = top;
+                cur = newv;
+                __syncwarp();
             }
-            if (in_row && c >= 1 && c <= N - 2) {
-                if (ORIENT == EQ_ADJUST_COLUMN && lane == 0 && b > 0) {
-                    // cell (c, j0-1) of the band above takes -R_k(c, j0) when its code says DOWN
-                    const unsigned code0 = sm.cs[(c >> 5) & (LSX_SLOTS - 1)][0][c & 31] & 12u;
-                    if (code0 == EQ_CODE_COL_DOWN) x[(size_t)(j0 - 1) * P + c] = -newv;
-                }
-                if (lane == 31) sm.rawbuf[c & 63] = newv;
-            }
-            prev2 = cur;
-            prev_up = top;
-            cur = newv;
-            __syncwarp();
         }
 
         if (m >= 1 && m - 1 < NC) {          // columns < 32m are final for every lane
@@ -250,16 +320,15 @@ __device__ __forceinline__ bool lsx_run_job(const LsxParams &p, const LsxProblem
     publish((unsigned)NC);
     cp_async_wait<0>();
     __syncwarp();
-#undef XS
     return true;
 }
 
 // One warp per CTA; persistent CTAs pull jobs from the ticket counter.
 __global__ void __launch_bounds__(32) k_linsolve_exact(const LsxParams p) {
     EQ_DYN_SMEM(lsx_smem_raw);
-    LsxSmem &sm = *reinterpret_cast<LsxSmem *>(lsx_smem_raw);
+    const uint32_t sbase = smem_u32(lsx_smem_raw);
     const int total = p.njobs * p.nprob;
-    if (threadIdx.x == 0) sm.rawbuf[0] = 0.f;   // column 0 of the raw stream is never produced
+    if (threadIdx.x == 0) sts_f32(sbase + LSX_RAW_OFF, 0.f);   // column 0 of the raw stream is never produced
     for (;;) {
         if (ld_volatile_s32(p.error) != 0) break;
         unsigned t = 0;
@@ -271,9 +340,9 @@ __global__ void __launch_bounds__(32) k_linsolve_exact(const LsxParams p) {
         const int k = (int)(jb >> 16), b = (int)(jb & 0xffffu);
         const LsxProblem &pr = p.prob[pi];
         bool ok;
-        if (pr.orient == EQ_ADJUST_ROW) ok = lsx_run_job<EQ_ADJUST_ROW>(p, pr, sm, b, k);
-        else if (pr.orient == EQ_ADJUST_COLUMN) ok = lsx_run_job<EQ_ADJUST_COLUMN>(p, pr, sm, b, k);
-        else ok = lsx_run_job<EQ_PASSIVE>(p, pr, sm, b, k);
+        if (pr.orient == EQ_ADJUST_ROW) ok = lsx_run_job<EQ_ADJUST_ROW>(p, pr, sbase, b, k);
+        else if (pr.orient == EQ_ADJUST_COLUMN) ok = lsx_run_job<EQ_ADJUST_COLUMN>(p, pr, sbase, b, k);
+        else ok = lsx_run_job<EQ_PASSIVE>(p, pr, sbase, b, k);
         if (!ok) break;
     }
 }

@@ -27,7 +27,7 @@ __device__ __forceinline__ unsigned eq_cell_code(const uint8_t *cells, int i, in
 
 // pass 0: codes + row/column "has fluid" flags + counts; pass 1: fill the lists
 __global__ void k_build_codes(const uint8_t *__restrict__ cells, uint8_t *__restrict__ codes,
-                              uint8_t *row_fluid, uint8_t *col_fluid, unsigned *counts,
+                              uint8_t *row_fluid, uint8_t *col_fluid, uint8_t *chunk_flags, unsigned *counts,
                               uint2 *row_list, uint2 *col_list, int pass, EqLayout L) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y;
@@ -40,8 +40,18 @@ __global__ void k_build_codes(const uint8_t *__restrict__ cells, uint8_t *__rest
             row_fluid[j] = 1;
             col_fluid[i] = 1;
         }
-        if (code & 3u) atomicAdd(&counts[0], 1u);
-        if (code & 12u) atomicAdd(&counts[1], 1u);
+        // (band, chunk) summaries for the wavefront solver: band = 32 rows from row 1, chunk = 32 columns
+        const int NB = (L.N - 2 + 31) / 32, NC = (L.N + 31) / 32;
+        if (code & 3u) {
+            atomicAdd(&counts[0], 1u);
+            chunk_flags[(size_t)((j - 1) / 32) * NC + i / 32] = 1;
+        }
+        if (code & 12u) {
+            atomicAdd(&counts[1], 1u);
+            chunk_flags[(size_t)NB * NC + (size_t)((j - 1) / 32) * NC + i / 32] = 1;
+            if (j / 32 < NB)   // row j is also row j0-1 of the band below (cross-band DOWN patch)
+                chunk_flags[(size_t)NB * NC + (size_t)(j / 32) * NC + i / 32] = 1;
+        }
     } else {
         if (code & 3u) {
             const unsigned slot = atomicAdd(&counts[2], 1u);

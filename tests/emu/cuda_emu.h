@@ -123,6 +123,15 @@ static inline unsigned ld_acquire_u32(const unsigned *p) { return __atomic_load_
 static inline void st_release_u32(unsigned *p, unsigned v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 static inline int ld_volatile_s32(const int *p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
 static inline void cp_async_16(void *smem, const void *gmem) { memcpy(smem, gmem, 16); }
+static inline unsigned ld_relaxed_u32(const unsigned *p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
+static inline void fence_acq_rel_gpu() { std::atomic_thread_fence(std::memory_order_acq_rel); }
+// "shared addresses" are byte offsets into the CTA's dynamic shared memory
+static inline uint32_t smem_u32(const void *p) { return (uint32_t)(static_cast<const unsigned char *>(p) - eq_emu::dyn_smem()); }
+static inline float lds_f32(uint32_t a) { float v; memcpy(&v, eq_emu::dyn_smem() + a, 4); return v; }
+static inline void sts_f32(uint32_t a, float v) { memcpy(eq_emu::dyn_smem() + a, &v, 4); }
+static inline unsigned lds_u8(uint32_t a) { return eq_emu::dyn_smem()[a]; }
+static inline float4 lds_f32x4(uint32_t a) { float4 v; memcpy(&v, eq_emu::dyn_smem() + a, 16); return v; }
+static inline void cp_async_16s(uint32_t saddr, const void *gmem) { memcpy(eq_emu::dyn_smem() + saddr, gmem, 16); }
 static inline void cp_async_commit() {}
 template <int N>
 static inline void cp_async_wait() {}

@@ -25,12 +25,21 @@ def random_rects(n: int, count: int, seed: int):
     return out
 
 
+def _canon(a: np.ndarray) -> np.ndarray:
+    """uint32 view with every NaN mapped to one pattern: NaN *payload and sign* are the only
+    bits not compared (x86 SSE produces 0xFFC00000 for an invalid operation, the GPU
+    0x7FFFFFFF; IEEE 754 leaves the payload open and the reference never inspects it)."""
+    u = np.ascontiguousarray(a).view(np.uint32).copy()
+    u[np.isnan(a)] = 0x7FC00000
+    return u
+
+
 def bits_equal(a: np.ndarray, b: np.ndarray) -> bool:
-    return np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    return np.array_equal(_canon(a), _canon(b))
 
 
 def describe_diff(a, b):
-    bad = np.argwhere(a.view(np.uint32) != b.view(np.uint32))
+    bad = np.argwhere(_canon(a) != _canon(b))
     return f"{len(bad)} cells differ, first (row, col): {bad[:5].tolist()}"
 
 

@@ -22,6 +22,14 @@ def test_lin_solve_exact(oracle, emu_lib, orient, n, k, rects):
     P.check_lin_solve(oracle, emu_lib, n, k, rects, orient)
 
 
+@pytest.mark.parametrize("orient", [P.ROW, P.COL, P.PASSIVE])
+def test_lin_solve_exact_fast_and_general_macro_steps(oracle, emu_lib, orient):
+    # N >= 97 is needed for a macro step with every lane on interior columns; with one small
+    # rectangle most (band, chunk) pairs are code-free and take the branch-free fast loop,
+    # the ones around the rectangle, the frame columns and the ragged last band do not.
+    P.check_lin_solve(oracle, emu_lib, 168, 2, [(100, 70, 108, 101)], orient)
+
+
 def test_lin_solve_zero_iterations_is_a_no_op(oracle, emu_lib):
     P.check_lin_solve(oracle, emu_lib, 32, 0, [], P.ROW)
 
