@@ -285,7 +285,7 @@ static int lin_solve_exact(eq_fluid *h, const LinSolveReq *req, int nreq, int64_
         CU(cudaMemsetAsync(h->flags, 0, sizeof(unsigned), h->stream));
         CU(cudaMemsetAsync(h->flags + 8, 0, (size_t)nreq * prog_words * sizeof(unsigned), h->stream));
         const int grid = std::min(h->lsx_ctas, p.njobs * nreq);
-        EQ_LAUNCH(k_linsolve_exact, grid, 32, LSX_SMEM_BYTES, h->stream, p);
+        EQ_LAUNCH(k_linsolve_exact, grid, LSX_THREADS, LSX_SMEM_BYTES, h->stream, p);
         TRY(check_launch("k_linsolve_exact"));
         done += kc;
     }
@@ -471,7 +471,7 @@ static int alloc_handle(const EqParams *params, eq_fluid **out) {
     CU(cudaMemsetAsync(h->flags, 0, h->flags_words * sizeof(unsigned), h->stream));
     CU(cudaFuncSetAttribute(k_linsolve_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LSX_SMEM_BYTES));
     int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_linsolve_exact, 32, LSX_SMEM_BYTES));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_linsolve_exact, LSX_THREADS, LSX_SMEM_BYTES));
     h->lsx_ctas = std::max(1, per_sm) * h->sm_count;
     return EQ_OK;
 }

@@ -98,6 +98,34 @@ __device__ __forceinline__ float4 lds_f32x4(uint32_t a) {
 __device__ __forceinline__ void cp_async_16s(uint32_t saddr, const void *gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(gmem) : "memory");
 }
+// mbarrier (shared::cta) -- each barrier gets a 16-byte slot (8 used on the device)
+__device__ __forceinline__ void mbar_init(uint32_t a, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t a) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t a, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t}"
+        : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    return ok != 0;
+}
+// arrive on the mbarrier once all cp.async of the executing thread issued so far have landed
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t a) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(a) : "memory");
+}
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
 #endif  // !EQ_HOST_EMU
 
 // The Gauss-Seidel update of fluid.rs:315-320 with the reference's expression

@@ -132,6 +132,28 @@ static inline void sts_f32(uint32_t a, float v) { memcpy(eq_emu::dyn_smem() + a,
 static inline unsigned lds_u8(uint32_t a) { return eq_emu::dyn_smem()[a]; }
 static inline float4 lds_f32x4(uint32_t a) { float4 v; memcpy(&v, eq_emu::dyn_smem() + a, 16); return v; }
 static inline void cp_async_16s(uint32_t saddr, const void *gmem) { memcpy(eq_emu::dyn_smem() + saddr, gmem, 16); }
+static inline void sts_u32(uint32_t a, uint32_t v) { memcpy(eq_emu::dyn_smem() + a, &v, 4); }
+static inline uint32_t lds_u32(uint32_t a) { uint32_t v; memcpy(&v, eq_emu::dyn_smem() + a, 4); return v; }
+// mbarrier stand-in: 16-byte slot {pending, phase, count}
+struct eq_emu_mbar { std::atomic<uint32_t> pending, phase; uint32_t count, pad; };
+static inline eq_emu_mbar *eq_emu_mb(uint32_t a) { return reinterpret_cast<eq_emu_mbar *>(eq_emu::dyn_smem() + a); }
+static inline void mbar_init(uint32_t a, uint32_t count) {
+    eq_emu_mbar *m = eq_emu_mb(a);
+    m->pending.store(count); m->phase.store(0); m->count = count;
+}
+static inline void mbar_arrive(uint32_t a) {
+    eq_emu_mbar *m = eq_emu_mb(a);
+    if (m->pending.fetch_sub(1, std::memory_order_acq_rel) == 1) {
+        m->pending.store(m->count, std::memory_order_relaxed);
+        m->phase.fetch_add(1, std::memory_order_release);
+    }
+}
+static inline bool mbar_try_wait(uint32_t a, uint32_t parity) {
+    if ((eq_emu_mb(a)->phase.load(std::memory_order_acquire) & 1u) != parity) return true;
+    std::this_thread::yield();
+    return false;
+}
+static inline void cp_async_mbar_arrive_noinc(uint32_t a) { mbar_arrive(a); }
 static inline void cp_async_commit() {}
 template <int N>
 static inline void cp_async_wait() {}
