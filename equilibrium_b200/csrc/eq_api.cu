@@ -163,7 +163,7 @@ static int ensure_tables(eq_fluid *h) {
     const EqLayout L = h->L;
     CU(cudaMemsetAsync(h->counts, 0, 4 * sizeof(unsigned), h->stream));
     CU(cudaMemsetAsync(h->row_fluid, 0, L.N, h->stream));
-    CU(cudaMemsetAsync(h->col_fluid, 0, L.N, h->stream));
+    CU(cudaMemsetAsync(h->col_fluid, 0, L.P, h->stream));
     CU(cudaMemsetAsync(h->chunk_flags, 0, 2 * (size_t)((L.N - 2 + 31) / 32) * ((L.N + 31) / 32), h->stream));
     EQ_LAUNCH(k_build_codes, row_grid(h, L.N), 256, 0, h->stream, h->cells, h->codes, h->row_fluid, h->col_fluid,
               h->chunk_flags, h->counts, nullptr, nullptr, 0, L);
@@ -458,7 +458,7 @@ static int alloc_handle(const EqParams *params, eq_fluid **out) {
     CU(cudaMalloc(&h->codes, elems));
     CU(cudaMemsetAsync(h->codes, 0, elems, h->stream));
     CU(cudaMalloc(&h->row_fluid, h->L.N));
-    CU(cudaMalloc(&h->col_fluid, h->L.N));
+    CU(cudaMalloc(&h->col_fluid, h->L.P));
     CU(cudaMalloc(&h->counts, 4 * sizeof(unsigned)));
     CU(cudaMalloc(&h->chunk_flags, 2 * (size_t)((h->L.N - 2 + 31) / 32) * ((h->L.N + 31) / 32)));
     const int NB = (h->L.N - 2 + 31) / 32;

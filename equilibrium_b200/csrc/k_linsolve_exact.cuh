@@ -162,13 +162,22 @@ struct LsxJob {
     __device__ __forceinline__ uint32_t bar_full(int q) const { return sbase + LSX_BAR_OFF + (uint32_t)(q & 3) * 16u; }
     __device__ __forceinline__ uint32_t bar_done(int q) const { return sbase + LSX_BAR_OFF + 64u + (uint32_t)(q & 3) * 16u; }
     __device__ __forceinline__ uint32_t bar_free(int q) const { return sbase + LSX_BAR_OFF + 128u + (uint32_t)(q & 3) * 16u; }
-    // macro step m can take the fast loop iff every lane stays on interior columns with an
-    // interior column to finalise, the band is full, no Passive frame row is involved and
-    // chunks m-1, m carry no fix-up code of this orientation.
-    __device__ __forceinline__ bool fast_ok(int m) const {
-        if (m < 2 || 32 * m + 31 > N - 2 || !full_band) return false;
-        if (ORIENT == EQ_PASSIVE) return b != 0 && !last_band;
-        return (cflags[m - 1] | cflags[m]) == 0;
+    // How macro step m (steps 32m..32m+31, columns 32m-31..32m+31) is executed:
+    //   EDGE   some lane is on/next to a frame column: fully general loop (first two and last few macro steps)
+    //   CODED  interior columns, but chunks m-1/m hold fix-up codes of this orientation, or (Passive)
+    //          the band owns a frame row: branch-light loop that reads one code byte per step
+    //   FAST   interior columns, nothing to fix up: 3 LDS + 1 SHFL + 6 FP + 1 STS per step
+    // Every job runs at the pace of the slowest job it depends on, so CODED must stay close to FAST.
+    enum { MODE_FAST = 0, MODE_CODED = 1, MODE_EDGE = 2 };
+    __device__ __forceinline__ int macro_mode(int m) const {
+        if (m < 2 || 32 * m + 31 > N - 2) return MODE_EDGE;
+        if (ORIENT == EQ_PASSIVE) return (b == 0 || last_band) ? MODE_CODED : MODE_FAST;
+        return (cflags[m - 1] | cflags[m]) ? MODE_CODED : MODE_FAST;
+    }
+    // the code tile of chunk q is read by macro steps q and q+1
+    __device__ __forceinline__ bool need_codes(int q) const {
+        if (ORIENT == EQ_PASSIVE) return b == 0 || last_band;      // row 0 of the tile carries col_fluid
+        return macro_mode(q) != MODE_FAST || macro_mode(q + 1) != MODE_FAST;
     }
 
     // ------------------------------------------------------------------ LOADER warp
@@ -205,15 +214,22 @@ struct LsxJob {
                 }
             }
             // codes rows j0-1 .. j0+31 (2 lanes x 16 B per row), skipped when both macro steps
-            // that touch this chunk take the fast loop
-            if (ORIENT != EQ_PASSIVE && !(fast_ok(q) && fast_ok(q + 1))) {
-                const int sub = lane & 1, rr = lane >> 1;
+            // that touch this chunk take the fast loop.  Passive has no codes; a band that owns a
+            // frame row stages col_fluid (quirk Q6) in row 0 of the code tile instead.
+            if (need_codes(q)) {
+                if (ORIENT == EQ_PASSIVE) {
+                    if (lane < 2)
+                        cp_async_16s(sbase + LSX_CS_OFF + (uint32_t)(q & 3) * 32u + 16u * lane,
+                                     p.col_fluid + col0 + 16 * lane);
+                } else {
+                    const int sub = lane & 1, rr = lane >> 1;
 #pragma unroll
-                for (int g = 0; g < 3; ++g) {
-                    const int t = 16 * g + rr;
-                    if (t < LSX_CROWS)
-                        cp_async_16s(sbase + LSX_CS_OFF + (uint32_t)t * 128u + (uint32_t)(q & 3) * 32u + 16u * sub,
-                                     p.codes + (size_t)(j0 - 1 + t) * P + col0 + 16 * sub);
+                    for (int g = 0; g < 3; ++g) {
+                        const int t = 16 * g + rr;
+                        if (t < LSX_CROWS)
+                            cp_async_16s(sbase + LSX_CS_OFF + (uint32_t)t * 128u + (uint32_t)(q & 3) * 32u + 16u * sub,
+                                         p.codes + (size_t)(j0 - 1 + t) * P + col0 + 16 * sub);
+                    }
                 }
             }
             cp_async_mbar_arrive_noinc(bar_full(q));     // fires when this lane's copies have landed
@@ -278,27 +294,76 @@ struct LsxJob {
             // macro step m reads chunks m-1, m, m+1
             if (m + 1 < NC && !lsx_wait_bar(bar_full(m + 1), (uint32_t)(((m + 1) >> 2) & 1), p.error, lane)) return false;
 
-            if (fast_ok(m)) {
-                // ---- fast loop: all lanes interior, no fix-ups ------------------------------------
+            const int mode = macro_mode(m);
+            if (mode != MODE_EDGE) {
+                // ---- interior columns: every lane computes and finalises an interior cell ---------
                 uint32_t o = ((uint32_t)(32 * m - lane) & 127u) << 2;      // byte offset of column c
                 uint32_t om1 = (o - 4u) & 508u;                            // column c-1
+                if (mode == MODE_FAST) {
 #pragma unroll 4
-                for (int t = 0; t < 32; ++t) {
-                    const uint32_t o1 = (o + 4u) & 508u;
-                    float up = __shfl_up_sync(0xffffffffu, cur, 1);
-                    const float right = lds_f32(xs_row + o1);
-                    const float down = lds_f32(xs_row + 512u + o);
-                    const float x0v = lds_f32(x0_row + o);
-                    if (lane == 0) up = lds_f32(xs_top + o);
-                    const float newv = gs_update(x0v, right, cur, down, up, a, c_recip);
-                    sts_f32(xs_row + om1, cur);                            // column c-1 is final: F = R
-                    if (lane == 31) sts_f32(raw_s + o, newv);
-                    prev2 = cur;
-                    prev_up = up;
-                    cur = newv;
-                    om1 = o;
-                    o = o1;
-                    __syncwarp();
+                    for (int t = 0; t < 32; ++t) {
+                        const uint32_t o1 = (o + 4u) & 508u;
+                        float up = __shfl_up_sync(0xffffffffu, cur, 1);
+                        const float right = lds_f32(xs_row + o1);
+                        const float down = lds_f32(xs_row + 512u + o);
+                        const float x0v = lds_f32(x0_row + o);
+                        if (lane == 0) up = lds_f32(xs_top + o);
+                        const float newv = gs_update(x0v, right, cur, down, up, a, c_recip);
+                        if (in_row) sts_f32(xs_row + om1, cur);                // column c-1 is final: F = R
+                        if (lane == 31) sts_f32(raw_s + o, newv);
+                        prev2 = cur;
+                        prev_up = up;
+                        cur = newv;
+                        om1 = o;
+                        o = o1;
+                        __syncwarp();
+                    }
+                } else {
+                    int c = 32 * m - lane;
+#pragma unroll 2
+                    for (int t = 0; t < 32; ++t, ++c) {
+                        const uint32_t o1 = (o + 4u) & 508u;
+                        float up = __shfl_up_sync(0xffffffffu, cur, 1);
+                        const float right = lds_f32(xs_row + o1);
+                        const float down = lds_f32(xs_row + 512u + o);
+                        const float x0v = lds_f32(x0_row + o);
+                        if (lane == 0) up = lds_f32(xs_top + o);
+                        float newv = gs_update(x0v, right, cur, down, up, a, c_recip);
+                        float F = cur;                                         // R_k(c-1, j)
+                        if (ORIENT == EQ_ADJUST_ROW) {
+                            const unsigned code = lds_u8(cs_row + (om1 >> 2)) & 3u;
+                            F = (code == EQ_CODE_ROW_RIGHT) ? -newv : ((code == EQ_CODE_ROW_LEFT) ? -prev2 : cur);
+                        } else if (ORIENT == EQ_ADJUST_COLUMN) {
+                            if (!in_row) newv = lds_f32(xs_row + o);           // frame row N-1 passes through
+                            const float dn = __shfl_down_sync(0xffffffffu, newv, 1);
+                            const unsigned code = lds_u8(cs_row + (om1 >> 2)) & 12u;
+                            if (code == EQ_CODE_COL_UP) F = -prev_up;
+                            else if (code == EQ_CODE_COL_DOWN) {
+                                if (lane < 31) F = -dn;
+                                else if (last_band) F = -lds_f32(xs_top + 33u * 512u + om1);
+                                // else: the band below patches this cell
+                            }
+                            if (lane == 0 && b > 0) {
+                                // cell (c, j0-1) of the band above takes -R_k(c, j0) when its code says DOWN
+                                const unsigned code0 = lds_u8(cs_top + (o >> 2)) & 12u;
+                                if (code0 == EQ_CODE_COL_DOWN) x[(size_t)(j0 - 1) * P + c] = -newv;
+                            }
+                        } else {
+                            // Passive band that owns a frame row (fluid.rs:182-183, conditional per Q6)
+                            if ((j == 1 || j == N - 2) && lds_u8(cs_top + (om1 >> 2))) {
+                                if (j == 1) sts_f32(xs_top + om1, cur);
+                                if (j == N - 2) sts_f32(xs_row + 512u + om1, cur);
+                            }
+                        }
+                        if (in_row) sts_f32(xs_row + om1, F);
+                        if (lane == 31 && in_row) sts_f32(raw_s + o, newv);
+                        prev2 = cur;
+                        prev_up = up;
+                        cur = newv;
+                        om1 = o;
+                        o = o1;
+                        __syncwarp();
+                    }
                 }
             } else {
                 // ---- general loop: frame columns, fix-ups, Passive frame copies ----------------------
@@ -345,7 +410,7 @@ struct LsxJob {
                                 if (cf == 1) sts_f32(xs_row, cur);
                                 if (cf == N - 2) sts_f32(xs_row + (((uint32_t)(N - 1) & 127u) << 2), cur);
                             }
-                            if ((j == 1 || j == N - 2) && p.col_fluid[cf]) {
+                            if ((j == 1 || j == N - 2) && lds_u8(cs_top + (om1 >> 2))) {
                                 if (j == 1) sts_f32(xs_top + om1, cur);
                                 if (j == N - 2) sts_f32(xs_row + 512u + om1, cur);
                             }
