@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <cmath>
@@ -83,6 +84,7 @@ struct eq_fluid {
     size_t flags_words;
     std::map<int, uint32_t *> *job_tables;   // keyed by iterations-per-launch
     int lsx_ctas;
+    unsigned long long *lsx_stats;   // EQ_LSX_STATS=1: device cycle counters of the wavefront kernel
     // timing / profiling
     cudaEvent_t ev0, ev1;
     bool prof_on;
@@ -164,7 +166,7 @@ static int ensure_tables(eq_fluid *h) {
     CU(cudaMemsetAsync(h->counts, 0, 4 * sizeof(unsigned), h->stream));
     CU(cudaMemsetAsync(h->row_fluid, 0, L.N, h->stream));
     CU(cudaMemsetAsync(h->col_fluid, 0, L.P, h->stream));
-    CU(cudaMemsetAsync(h->chunk_flags, 0, 2 * (size_t)((L.N - 2 + 31) / 32) * ((L.N + 31) / 32), h->stream));
+    CU(cudaMemsetAsync(h->chunk_flags, 0, 2 * (size_t)((L.N - 2 + 31) / 32) * ((L.N + EQ_LSX_CW - 1) / EQ_LSX_CW), h->stream));
     EQ_LAUNCH(k_build_codes, row_grid(h, L.N), 256, 0, h->stream, h->cells, h->codes, h->row_fluid, h->col_fluid,
               h->chunk_flags, h->counts, nullptr, nullptr, 0, L);
     TRY(check_launch("k_build_codes"));
@@ -249,7 +251,7 @@ static int get_job_table(eq_fluid *h, int kc, const uint32_t **out) {
 static int lin_solve_exact(eq_fluid *h, const LinSolveReq *req, int nreq, int64_t iters) {
     const EqLayout L = h->L;
     const int NB = (L.N - 2 + 31) / 32;
-    const int NC = (L.N + 31) / 32;
+    const int NC = (L.N + EQ_LSX_CW - 1) / EQ_LSX_CW;
     int64_t done = 0;
     while (done < iters) {
         const int kc = (int)std::min<int64_t>(LSX_KMAX, iters - done);
@@ -281,6 +283,7 @@ static int lin_solve_exact(eq_fluid *h, const LinSolveReq *req, int nreq, int64_
         p.NC = NC;
         p.ticket = h->flags;
         p.error = reinterpret_cast<int *>(h->flags + 1);
+        p.stats = h->lsx_stats;
         // ticket := 0, progress := 0; the sticky error word is left alone
         CU(cudaMemsetAsync(h->flags, 0, sizeof(unsigned), h->stream));
         CU(cudaMemsetAsync(h->flags + 8, 0, (size_t)nreq * prog_words * sizeof(unsigned), h->stream));
@@ -460,7 +463,7 @@ static int alloc_handle(const EqParams *params, eq_fluid **out) {
     CU(cudaMalloc(&h->row_fluid, h->L.N));
     CU(cudaMalloc(&h->col_fluid, h->L.P));
     CU(cudaMalloc(&h->counts, 4 * sizeof(unsigned)));
-    CU(cudaMalloc(&h->chunk_flags, 2 * (size_t)((h->L.N - 2 + 31) / 32) * ((h->L.N + 31) / 32)));
+    CU(cudaMalloc(&h->chunk_flags, 2 * (size_t)((h->L.N - 2 + 31) / 32) * ((h->L.N + EQ_LSX_CW - 1) / EQ_LSX_CW)));
     const int NB = (h->L.N - 2 + 31) / 32;
     for (int i = 0; i < 2; ++i) {
         CU(cudaMalloc(&h->raw[i], (size_t)NB * h->L.P * sizeof(float)));
@@ -473,6 +476,11 @@ static int alloc_handle(const EqParams *params, eq_fluid **out) {
     int per_sm = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_linsolve_exact, LSX_THREADS, LSX_SMEM_BYTES));
     h->lsx_ctas = std::max(1, per_sm) * h->sm_count;
+    if (const char *e = getenv("EQ_LSX_CTAS_PER_SM")) h->lsx_ctas = std::max(1, std::min(per_sm, atoi(e))) * h->sm_count;
+    if (getenv("EQ_LSX_STATS")) {
+        CU(cudaMalloc(&h->lsx_stats, 16 * sizeof(unsigned long long)));
+        CU(cudaMemsetAsync(h->lsx_stats, 0, 16 * sizeof(unsigned long long), h->stream));
+    }
     return EQ_OK;
 }
 
@@ -540,6 +548,7 @@ int eq_destroy(eq_fluid *h) {
     cudaFree(h->col_fluid);
     cudaFree(h->counts);
     cudaFree(h->chunk_flags);
+    cudaFree(h->lsx_stats);
     cudaFree(h->row_list);
     cudaFree(h->col_list);
     cudaFree(h->raw[0]);
@@ -698,6 +707,20 @@ int eq_step_n(eq_fluid *h, int64_t n, const EqSource *sources, int64_t n_sources
     return EQ_OK;
 }
 
+static void dump_lsx_stats(eq_fluid *h) {
+    if (!h->lsx_stats) return;
+    unsigned long long v[16];
+    if (cudaMemcpy(v, h->lsx_stats, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return;
+    cudaMemset(h->lsx_stats, 0, sizeof(v));
+    const char *names[16] = {"compute.wait_full", "compute.fast", "compute.coded", "compute.edge", "n.fast", "n.coded",
+                             "n.edge", "loader.wait_free", "loader.wait_flags", "-", "storer.wait_done", "storer.store",
+                             "storer.release", "-", "-", "-"};
+    fprintf(stderr, "[lsx stats, Mcycles summed over jobs]");
+    for (int i = 0; i < 13; ++i)
+        if (names[i][0] != '-') fprintf(stderr, " %s=%.1f", names[i], (i >= 4 && i <= 6) ? (double)v[i] : v[i] / 1e6);
+    fprintf(stderr, "\n");
+}
+
 static int check_device_error(eq_fluid *h) {
     int err = 0;
     CU(cudaMemcpyAsync(&err, h->flags + 1, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
@@ -709,6 +732,7 @@ static int check_device_error(eq_fluid *h) {
 int eq_sync(eq_fluid *h) {
     NEED(h);
     CU(cudaStreamSynchronize(h->stream));
+    dump_lsx_stats(h);
     return check_device_error(h);
 }
 

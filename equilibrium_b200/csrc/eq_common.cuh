@@ -21,6 +21,9 @@
 #endif
 
 #define EQ_ROW_PAD 32
+#ifndef EQ_LSX_CW
+#define EQ_LSX_CW 16   // chunk width (columns) of the wavefront solver: staging / write-back / flag granularity
+#endif
 
 // cells_type / derived per-cell codes (one byte per cell, same pitch P):
 //   bits 0-1  AdjustRow fix-up:    0 none, 1 take -x[i-1,j], 2 take -x[i+1,j]   (fluid.rs:151-164)
@@ -110,6 +113,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t a, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred P1;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t}"
+        : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    return ok != 0;
+}
+// non-blocking probe (try_wait may suspend the thread for a while)
+__device__ __forceinline__ bool mbar_test_wait(uint32_t a, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, P1;\n\t}"
         : "=r"(ok) : "r"(a), "r"(parity) : "memory");
     return ok != 0;

@@ -59,8 +59,12 @@
 #define LSX_X0_OFF (LSX_XROWS * 512u)
 #define LSX_CS_OFF (LSX_X0_OFF + 32u * 512u)
 #define LSX_RAW_OFF (LSX_CS_OFF + LSX_CROWS * 128u)    // 128-float ring of the raw stream (lane 31's results)
-#define LSX_BAR_OFF (LSX_RAW_OFF + 128u * 4u)          // mbarriers: full[4], done[4], free[4], 16 B each
-#define LSX_MISC_OFF (LSX_BAR_OFF + 12u * 16u)         // [0] ticket broadcast
+#define LSX_CW EQ_LSX_CW                               // chunk width in columns (16): unit of staging,
+                                                       // of write-back and of the progress flags
+#define LSX_SLOTS (128 / LSX_CW)                       // the 128-column ring holds this many chunks
+#define LSX_BACK (32 / LSX_CW)                         // after macro step m, chunk m-LSX_BACK is final
+#define LSX_BAR_OFF (LSX_RAW_OFF + 128u * 4u)          // mbarriers: full[], done[], free[], 16 B each
+#define LSX_MISC_OFF (LSX_BAR_OFF + 3u * LSX_SLOTS * 16u)   // [0] ticket broadcast
 #define LSX_SMEM_BYTES (LSX_MISC_OFF + 16u)
 #define LSX_THREADS 96
 #define LSX_SPIN_LIMIT (1u << 22)
@@ -86,7 +90,15 @@ struct LsxParams {
     int N, P, K, NB, NC;
     unsigned *ticket;
     int *error;
+    unsigned long long *stats;   // optional [16] cycle counters (EQ_LSX_STATS=1), see eq_api.cu
 };
+
+#ifdef EQ_HOST_EMU
+static inline long long lsx_clock() { return 0; }
+#else
+__device__ __forceinline__ long long lsx_clock() { return clock64(); }
+#endif
+#define LSX_STAT(slot, v) do { if (p.stats && lane == 0) atomicAdd(p.stats + (slot), (unsigned long long)(v)); } while (0)
 
 // ---- waiting primitives: lane 0 waits, the result is broadcast; every loop can be aborted ----
 // Dependency flags of other jobs (global memory, acquire).
@@ -146,7 +158,7 @@ struct LsxJob {
     uint32_t sbase;
     int b, k, lane;
     int N, P, NC, NB, j0, M;
-    bool last_band, full_band;
+    bool last_band;
     const uint8_t *cflags;
 
     __device__ __forceinline__ LsxJob(const LsxParams &p_, const LsxProblem &pr_, uint32_t sbase_, int b_, int k_,
@@ -154,30 +166,36 @@ struct LsxJob {
         : p(p_), pr(pr_), sbase(sbase_), b(b_), k(k_), lane(lane_) {
         N = p.N; P = p.P; NC = p.NC; NB = p.NB;
         j0 = 1 + 32 * b;
-        M = (N + 31 + 31) >> 5;                       // steps 0 .. N+30 in macro steps of 32
+        M = (N + 31 + LSX_CW - 1) / LSX_CW;           // steps 0 .. N+30 in macro steps of LSX_CW
         last_band = (b == NB - 1);
-        full_band = (j0 + 31 <= N - 2);
         cflags = p.chunk_flags + (ORIENT == EQ_ADJUST_COLUMN ? (size_t)NB * NC : 0) + (size_t)b * NC;
     }
-    __device__ __forceinline__ uint32_t bar_full(int q) const { return sbase + LSX_BAR_OFF + (uint32_t)(q & 3) * 16u; }
-    __device__ __forceinline__ uint32_t bar_done(int q) const { return sbase + LSX_BAR_OFF + 64u + (uint32_t)(q & 3) * 16u; }
-    __device__ __forceinline__ uint32_t bar_free(int q) const { return sbase + LSX_BAR_OFF + 128u + (uint32_t)(q & 3) * 16u; }
-    // How macro step m (steps 32m..32m+31, columns 32m-31..32m+31) is executed:
-    //   EDGE   some lane is on/next to a frame column: fully general loop (first two and last few macro steps)
-    //   CODED  interior columns, but chunks m-1/m hold fix-up codes of this orientation, or (Passive)
-    //          the band owns a frame row: branch-light loop that reads one code byte per step
+    __device__ __forceinline__ uint32_t bar_full(int q) const { return sbase + LSX_BAR_OFF + (uint32_t)(q % LSX_SLOTS) * 16u; }
+    __device__ __forceinline__ uint32_t bar_done(int q) const { return sbase + LSX_BAR_OFF + (uint32_t)(LSX_SLOTS + q % LSX_SLOTS) * 16u; }
+    __device__ __forceinline__ uint32_t bar_free(int q) const { return sbase + LSX_BAR_OFF + (uint32_t)(2 * LSX_SLOTS + q % LSX_SLOTS) * 16u; }
+    __device__ __forceinline__ uint32_t use_parity(int q) const { return (uint32_t)((q / LSX_SLOTS) & 1); }
+    // How macro step m (steps CW*m .. CW*m+CW-1; columns CW*m-31 .. CW*m+CW-1) is executed:
+    //   EDGE   some lane is on/next to a frame column: fully general loop (first and last few macro steps)
+    //   CODED  interior columns, but the chunks it finalises hold fix-up codes of this orientation, or
+    //          (Passive) the band owns a frame row: branch-light loop that reads one code byte per step
     //   FAST   interior columns, nothing to fix up: 3 LDS + 1 SHFL + 6 FP + 1 STS per step
     // Every job runs at the pace of the slowest job it depends on, so CODED must stay close to FAST.
     enum { MODE_FAST = 0, MODE_CODED = 1, MODE_EDGE = 2 };
     __device__ __forceinline__ int macro_mode(int m) const {
-        if (m < 2 || 32 * m + 31 > N - 2) return MODE_EDGE;
+        if (LSX_CW * m - 31 < 2 || LSX_CW * m + LSX_CW - 1 > N - 2) return MODE_EDGE;
         if (ORIENT == EQ_PASSIVE) return (b == 0 || last_band) ? MODE_CODED : MODE_FAST;
-        return (cflags[m - 1] | cflags[m]) ? MODE_CODED : MODE_FAST;
+        unsigned any = 0;
+#pragma unroll
+        for (int d = 0; d <= LSX_BACK; ++d) any |= cflags[m - d];     // codes are read in chunks m-BACK .. m
+        return any ? MODE_CODED : MODE_FAST;
     }
-    // the code tile of chunk q is read by macro steps q and q+1
+    // the code tile of chunk q is read by macro steps q .. q+LSX_BACK
     __device__ __forceinline__ bool need_codes(int q) const {
         if (ORIENT == EQ_PASSIVE) return b == 0 || last_band;      // row 0 of the tile carries col_fluid
-        return macro_mode(q) != MODE_FAST || macro_mode(q + 1) != MODE_FAST;
+        bool need = false;
+#pragma unroll
+        for (int d = 0; d <= LSX_BACK; ++d) need = need || (macro_mode(q + d) != MODE_FAST);
+        return need;
     }
 
     // ------------------------------------------------------------------ LOADER warp
@@ -187,48 +205,52 @@ struct LsxJob {
         const unsigned *flag_prev_iter = (k > 0) ? pr.progress + (size_t)(k - 1) * NB + min(b + 1, NB - 1) : nullptr;
         const unsigned *flag_band_above = (b > 0) ? pr.progress + (size_t)k * NB + (b - 1) : nullptr;
         const float *top_src = (b > 0) ? pr.raw + (size_t)b * P : x;  // row j0-1: raw stream or frame row 0
+        constexpr int LPR = LSX_CW / 4;            // lanes per row (16 B each)
+        constexpr int RPP = 32 / LPR;              // rows per pass
+        const int sub = lane % LPR, rr = lane / LPR;
         for (int q = 0; q < NC; ++q) {
-            // the ring slot must have been written back (chunk q-4) ...
-            if (q >= 4 && !lsx_wait_bar(bar_free(q), (uint32_t)(((q >> 2) - 1) & 1), p.error, lane)) return false;
+            const long long t0 = p.stats ? lsx_clock() : 0;
+            // the ring slot must have been written back (chunk q-SLOTS) ...
+            if (q >= LSX_SLOTS && !lsx_wait_bar(bar_free(q), use_parity(q - LSX_SLOTS), p.error, lane)) return false;
+            const long long t1 = p.stats ? lsx_clock() : 0;
             // ... and the producers of this chunk must have published it
             if (!lsx_wait_flags(flag_prev_iter, (unsigned)q + 1u, flag_band_above, (unsigned)q + 1u, p.error, lane))
                 return false;
-            const uint32_t slot = (uint32_t)(q & 3) * 128u;   // byte offset of the chunk inside a 512 B row
-            const int col0 = 32 * q;
-            {   // x rows j0-1 .. j0+32 : 8 lanes x 16 B per row, 4 rows per pass
-                const int sub = lane & 7, rr = lane >> 3;
+            if (p.stats) { const long long t2 = lsx_clock(); LSX_STAT(7, t1 - t0); LSX_STAT(8, t2 - t1); }
+            const uint32_t slot = (uint32_t)(q % LSX_SLOTS) * (LSX_CW * 4u);   // byte offset of the chunk in a 512 B row
+            const int col0 = LSX_CW * q;
+            // x rows j0-1 .. j0+32 and x0 rows j0 .. j0+31
 #pragma unroll
-                for (int g = 0; g < 9; ++g) {
-                    const int t = 4 * g + rr;
-                    if (t < LSX_XROWS) {
-                        const float *src = (t == 0) ? top_src + col0 + 4 * sub
-                                                    : x + (size_t)(j0 - 1 + t) * P + col0 + 4 * sub;
-                        cp_async_16s(sbase + LSX_XS_OFF + (uint32_t)t * 512u + slot + 16u * sub, src);
-                    }
-                }
-#pragma unroll
-                for (int g = 0; g < 8; ++g) {
-                    const int t = 4 * g + rr;
-                    cp_async_16s(sbase + LSX_X0_OFF + (uint32_t)t * 512u + slot + 16u * sub,
-                                 x0 + (size_t)(j0 + t) * P + col0 + 4 * sub);
+            for (int g = 0; g < (LSX_XROWS + RPP - 1) / RPP; ++g) {
+                const int t = RPP * g + rr;
+                if (t < LSX_XROWS) {
+                    const float *src = (t == 0) ? top_src + col0 + 4 * sub
+                                                : x + (size_t)(j0 - 1 + t) * P + col0 + 4 * sub;
+                    cp_async_16s(sbase + LSX_XS_OFF + (uint32_t)t * 512u + slot + 16u * sub, src);
                 }
             }
-            // codes rows j0-1 .. j0+31 (2 lanes x 16 B per row), skipped when both macro steps
-            // that touch this chunk take the fast loop.  Passive has no codes; a band that owns a
-            // frame row stages col_fluid (quirk Q6) in row 0 of the code tile instead.
-            if (need_codes(q)) {
-                if (ORIENT == EQ_PASSIVE) {
-                    if (lane < 2)
-                        cp_async_16s(sbase + LSX_CS_OFF + (uint32_t)(q & 3) * 32u + 16u * lane,
-                                     p.col_fluid + col0 + 16 * lane);
-                } else {
-                    const int sub = lane & 1, rr = lane >> 1;
 #pragma unroll
-                    for (int g = 0; g < 3; ++g) {
-                        const int t = 16 * g + rr;
+            for (int g = 0; g < 32 / RPP; ++g) {
+                const int t = RPP * g + rr;
+                cp_async_16s(sbase + LSX_X0_OFF + (uint32_t)t * 512u + slot + 16u * sub,
+                             x0 + (size_t)(j0 + t) * P + col0 + 4 * sub);
+            }
+            // codes rows j0-1 .. j0+31, skipped when every macro step that touches this chunk takes the
+            // fast loop.  Passive has no codes; a band that owns a frame row stages col_fluid (quirk Q6)
+            // in row 0 of the code tile instead.
+            if (need_codes(q)) {
+                constexpr int CLPR = LSX_CW / 16;   // lanes per code row
+                const uint32_t cslot = (uint32_t)(q % LSX_SLOTS) * LSX_CW;
+                if (ORIENT == EQ_PASSIVE) {
+                    if (lane < CLPR) cp_async_16s(sbase + LSX_CS_OFF + cslot + 16u * lane, p.col_fluid + col0 + 16 * lane);
+                } else {
+                    const int csub = lane % CLPR, crr = lane / CLPR;
+#pragma unroll
+                    for (int g = 0; g < (LSX_CROWS * CLPR + 31) / 32; ++g) {
+                        const int t = (32 / CLPR) * g + crr;
                         if (t < LSX_CROWS)
-                            cp_async_16s(sbase + LSX_CS_OFF + (uint32_t)t * 128u + (uint32_t)(q & 3) * 32u + 16u * sub,
-                                         p.codes + (size_t)(j0 - 1 + t) * P + col0 + 16 * sub);
+                            cp_async_16s(sbase + LSX_CS_OFF + (uint32_t)t * 128u + cslot + 16u * csub,
+                                         p.codes + (size_t)(j0 - 1 + t) * P + col0 + 16 * csub);
                     }
                 }
             }
@@ -243,29 +265,44 @@ struct LsxJob {
         unsigned *my_flag = pr.progress + (size_t)k * NB + b;
         float *raw_out = (b + 1 < NB) ? pr.raw + (size_t)(b + 1) * P : nullptr;
         const uint32_t raw_s = sbase + LSX_RAW_OFF;
-        const int sub = lane & 7, rr = lane >> 3;
+        constexpr int LPR = LSX_CW / 4, RPP = 32 / LPR;
+        const int sub = lane % LPR, rr = lane / LPR;
         // band rows (tile rows 1..32); the bottom frame row N-1 travels with the last band
         const int t_hi = last_band ? 33 : 32;
         const int t_lo = (ORIENT == EQ_PASSIVE && b == 0) ? 0 : 1;  // Passive rewrites frame row 0
-        for (int q = 0; q < NC; ++q) {
-            if (!lsx_wait_bar(bar_done(q), (uint32_t)((q >> 2) & 1), p.error, lane)) return false;
-            const uint32_t slot = (uint32_t)(q & 3) * 128u;
-            const int col0 = 32 * q;
+        int q = 0;
+        while (q < NC) {
+            const long long t0 = p.stats ? lsx_clock() : 0;
+            if (!lsx_wait_bar(bar_done(q), use_parity(q), p.error, lane)) return false;
+            const long long t1 = p.stats ? lsx_clock() : 0;
+            // write back every chunk that is already final (the release below is the expensive part:
+            // it waits for the stores to drain, so it is amortised over as many chunks as are ready)
+            for (;;) {
+                const uint32_t slot = (uint32_t)(q % LSX_SLOTS) * (LSX_CW * 4u);
+                const int col0 = LSX_CW * q;
 #pragma unroll
-            for (int g = 0; g < 9; ++g) {
-                const int t = 4 * g + rr;
-                const int row = j0 - 1 + t;
-                if (t >= t_lo && t <= t_hi && row <= N - 1) {
-                    const float4 v = lds_f32x4(sbase + LSX_XS_OFF + (uint32_t)t * 512u + slot + 16u * sub);
-                    *reinterpret_cast<float4 *>(x + (size_t)row * P + col0 + 4 * sub) = v;
+                for (int g = 0; g < (LSX_XROWS + RPP - 1) / RPP; ++g) {
+                    const int t = RPP * g + rr;
+                    const int row = j0 - 1 + t;
+                    if (t >= t_lo && t <= t_hi && row <= N - 1) {
+                        const float4 v = lds_f32x4(sbase + LSX_XS_OFF + (uint32_t)t * 512u + slot + 16u * sub);
+                        *reinterpret_cast<float4 *>(x + (size_t)row * P + col0 + 4 * sub) = v;
+                    }
                 }
+                if (raw_out && lane < LSX_CW) raw_out[col0 + lane] = lds_f32(raw_s + (uint32_t)((col0 + lane) & 127) * 4u);
+                __syncwarp();                             // every lane's smem reads of this slot are done
+                if (lane == 0) mbar_arrive(bar_free(q));  // the ring slot may be refilled
+                ++q;
+                if (q >= NC) break;
+                int more = 0;
+                if (lane == 0) more = mbar_test_wait(bar_done(q), use_parity(q)) ? 1 : 0;
+                more = __shfl_sync(0xffffffffu, more, 0);
+                if (!more) break;
             }
-            if (raw_out) raw_out[col0 + lane] = lds_f32(raw_s + (uint32_t)((col0 + lane) & 127) * 4u);
-            __syncwarp();                             // every lane's loads and stores are issued ...
-            if (lane == 0) {
-                mbar_arrive(bar_free(q));             // ... the ring slot may be refilled,
-                st_release_u32(my_flag, (unsigned)q + 1u);   // and the release makes the stores visible GPU-wide
-            }
+            const long long t2 = p.stats ? lsx_clock() : 0;
+            __syncwarp();
+            if (lane == 0) st_release_u32(my_flag, (unsigned)q);   // the release makes the stores visible GPU-wide
+            if (p.stats) { const long long t3 = lsx_clock(); LSX_STAT(10, t1 - t0); LSX_STAT(11, t2 - t1); LSX_STAT(12, t3 - t2); }
         }
         return true;
     }
@@ -291,17 +328,19 @@ struct LsxJob {
         float cur = 0.f, prev2 = 0.f, prev_up = 0.f;
 
         for (int m = 0; m < M; ++m) {
-            // macro step m reads chunks m-1, m, m+1
-            if (m + 1 < NC && !lsx_wait_bar(bar_full(m + 1), (uint32_t)(((m + 1) >> 2) & 1), p.error, lane)) return false;
+            // macro step m reads chunks m-LSX_BACK .. m+1
+            const long long tw0 = p.stats ? lsx_clock() : 0;
+            if (m + 1 < NC && !lsx_wait_bar(bar_full(m + 1), use_parity(m + 1), p.error, lane)) return false;
+            const long long tw1 = p.stats ? lsx_clock() : 0;
 
             const int mode = macro_mode(m);
             if (mode != MODE_EDGE) {
                 // ---- interior columns: every lane computes and finalises an interior cell ---------
-                uint32_t o = ((uint32_t)(32 * m - lane) & 127u) << 2;      // byte offset of column c
+                uint32_t o = ((uint32_t)(LSX_CW * m - lane) & 127u) << 2;  // byte offset of column c
                 uint32_t om1 = (o - 4u) & 508u;                            // column c-1
                 if (mode == MODE_FAST) {
 #pragma unroll 4
-                    for (int t = 0; t < 32; ++t) {
+                    for (int t = 0; t < LSX_CW; ++t) {
                         const uint32_t o1 = (o + 4u) & 508u;
                         float up = __shfl_up_sync(0xffffffffu, cur, 1);
                         const float right = lds_f32(xs_row + o1);
@@ -319,9 +358,9 @@ struct LsxJob {
                         __syncwarp();
                     }
                 } else {
-                    int c = 32 * m - lane;
+                    int c = LSX_CW * m - lane;
 #pragma unroll 2
-                    for (int t = 0; t < 32; ++t, ++c) {
+                    for (int t = 0; t < LSX_CW; ++t, ++c) {
                         const uint32_t o1 = (o + 4u) & 508u;
                         float up = __shfl_up_sync(0xffffffffu, cur, 1);
                         const float right = lds_f32(xs_row + o1);
@@ -367,8 +406,8 @@ struct LsxJob {
                 }
             } else {
                 // ---- general loop: frame columns, fix-ups, Passive frame copies ----------------------
-                const int s_end = min(32 * m + 32, S);
-                for (int s = 32 * m; s < s_end; ++s) {
+                const int s_end = min(LSX_CW * m + LSX_CW, S);
+                for (int s = LSX_CW * m; s < s_end; ++s) {
                     const int c = s - lane;          // column this lane computes now (0 = left frame cell)
                     const uint32_t o = ((uint32_t)c & 127u) << 2;
                     const uint32_t om1 = (o - 4u) & 508u;
@@ -430,11 +469,12 @@ struct LsxJob {
                     __syncwarp();
                 }
             }
-            // columns < 32m are final for every lane: hand chunk m-1 to the storer
-            if (m >= 1 && m - 1 < NC && lane == 0) mbar_arrive(bar_done(m - 1));
+            // every lane has finalised the columns below CW*(m+1)-32: hand that chunk to the storer
+            if (m >= LSX_BACK && m - LSX_BACK < NC && lane == 0) mbar_arrive(bar_done(m - LSX_BACK));
+            if (p.stats) { const long long tw2 = lsx_clock(); LSX_STAT(0, tw1 - tw0); LSX_STAT(1 + mode, tw2 - tw1); LSX_STAT(4 + mode, 1); }
         }
         if (lane == 0)
-            for (int q = max(M - 1, 0); q < NC; ++q) mbar_arrive(bar_done(q));
+            for (int q = max(M - LSX_BACK, 0); q < NC; ++q) mbar_arrive(bar_done(q));
         return true;
     }
 };
@@ -444,16 +484,18 @@ __global__ void __launch_bounds__(LSX_THREADS) k_linsolve_exact(const LsxParams 
     EQ_DYN_SMEM(lsx_smem_raw);
     const uint32_t sbase = smem_u32(lsx_smem_raw);
     const int total = p.njobs * p.nprob;
-    const int warp = (int)threadIdx.x >> 5, lane = (int)threadIdx.x & 31;
+    // broadcast the warp index so the compiler knows the role branches below are warp-uniform
+    // (otherwise every __shfl/__syncwarp in the roles becomes an out-of-line WARPSYNC.COLLECTIVE)
+    const int warp = __shfl_sync(0xffffffffu, (int)threadIdx.x >> 5, 0), lane = (int)threadIdx.x & 31;
     for (;;) {
         __syncthreads();                               // the previous job is finished in all three roles
         if (threadIdx.x == 0) {
             const unsigned t = (ld_volatile_s32(p.error) != 0) ? 0xffffffffu : atomicAdd(p.ticket, 1u);
             sts_u32(sbase + LSX_MISC_OFF, t);
-            for (int i = 0; i < 4; ++i) {
-                mbar_init(sbase + LSX_BAR_OFF + (uint32_t)i * 16u, 32u);          // full: 32 loader lanes
-                mbar_init(sbase + LSX_BAR_OFF + 64u + (uint32_t)i * 16u, 1u);     // done: compute lane 0
-                mbar_init(sbase + LSX_BAR_OFF + 128u + (uint32_t)i * 16u, 1u);    // free: storer lane 0
+            for (int i = 0; i < LSX_SLOTS; ++i) {
+                mbar_init(sbase + LSX_BAR_OFF + (uint32_t)i * 16u, 32u);                       // full: 32 loader lanes
+                mbar_init(sbase + LSX_BAR_OFF + (uint32_t)(LSX_SLOTS + i) * 16u, 1u);          // done: compute lane 0
+                mbar_init(sbase + LSX_BAR_OFF + (uint32_t)(2 * LSX_SLOTS + i) * 16u, 1u);      // free: storer lane 0
             }
         }
         __syncthreads();

@@ -40,17 +40,17 @@ __global__ void k_build_codes(const uint8_t *__restrict__ cells, uint8_t *__rest
             row_fluid[j] = 1;
             col_fluid[i] = 1;
         }
-        // (band, chunk) summaries for the wavefront solver: band = 32 rows from row 1, chunk = 32 columns
-        const int NB = (L.N - 2 + 31) / 32, NC = (L.N + 31) / 32;
+        // (band, chunk) summaries for the wavefront solver: band = 32 rows from row 1, chunk = EQ_LSX_CW columns
+        const int NB = (L.N - 2 + 31) / 32, NC = (L.N + EQ_LSX_CW - 1) / EQ_LSX_CW;
         if (code & 3u) {
             atomicAdd(&counts[0], 1u);
-            chunk_flags[(size_t)((j - 1) / 32) * NC + i / 32] = 1;
+            chunk_flags[(size_t)((j - 1) / 32) * NC + i / EQ_LSX_CW] = 1;
         }
         if (code & 12u) {
             atomicAdd(&counts[1], 1u);
-            chunk_flags[(size_t)NB * NC + (size_t)((j - 1) / 32) * NC + i / 32] = 1;
+            chunk_flags[(size_t)NB * NC + (size_t)((j - 1) / 32) * NC + i / EQ_LSX_CW] = 1;
             if (j / 32 < NB)   // row j is also row j0-1 of the band below (cross-band DOWN patch)
-                chunk_flags[(size_t)NB * NC + (size_t)(j / 32) * NC + i / 32] = 1;
+                chunk_flags[(size_t)NB * NC + (size_t)(j / 32) * NC + i / EQ_LSX_CW] = 1;
         }
     } else {
         if (code & 3u) {

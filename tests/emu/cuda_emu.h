@@ -153,10 +153,12 @@ static inline bool mbar_try_wait(uint32_t a, uint32_t parity) {
     std::this_thread::yield();
     return false;
 }
+static inline bool mbar_test_wait(uint32_t a, uint32_t parity) { return (eq_emu_mb(a)->phase.load(std::memory_order_acquire) & 1u) != parity; }
 static inline void cp_async_mbar_arrive_noinc(uint32_t a) { mbar_arrive(a); }
 static inline void cp_async_commit() {}
 template <int N>
 static inline void cp_async_wait() {}
+static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 static inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 static inline int atomicMin(int *p, int v) {
     int old = __atomic_load_n(p, __ATOMIC_RELAXED);
@@ -223,6 +225,8 @@ static inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cuda
     memcpy(d, s, n);
     return cudaSuccess;
 }
+static inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { memcpy(d, s, n); return cudaSuccess; }
+static inline cudaError_t cudaMemset(void *p, int v, size_t n) { memset(p, v, n); return cudaSuccess; }
 static inline cudaError_t cudaMemcpy2DAsync(void *d, size_t dp, const void *s, size_t sp, size_t w, size_t h,
                                             cudaMemcpyKind, cudaStream_t) {
     for (size_t r = 0; r < h; ++r) memcpy(static_cast<char *>(d) + r * dp, static_cast<const char *>(s) + r * sp, w);
