@@ -713,11 +713,11 @@ static void dump_lsx_stats(eq_fluid *h) {
     if (cudaMemcpy(v, h->lsx_stats, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return;
     cudaMemset(h->lsx_stats, 0, sizeof(v));
     const char *names[16] = {"compute.wait_full", "compute.fast", "compute.coded", "compute.edge", "n.fast", "n.coded",
-                             "n.edge", "loader.wait_free", "loader.wait_flags", "-", "storer.wait_done", "storer.store",
-                             "storer.release", "-", "-", "-"};
+                             "n.edge", "loader.wait_free", "loader.wait_flags", "n.releases", "storer.wait_done", "storer.store",
+                             "publisher.release", "-", "-", "-"};
     fprintf(stderr, "[lsx stats, Mcycles summed over jobs]");
     for (int i = 0; i < 13; ++i)
-        if (names[i][0] != '-') fprintf(stderr, " %s=%.1f", names[i], (i >= 4 && i <= 6) ? (double)v[i] : v[i] / 1e6);
+        if (names[i][0] != '-') fprintf(stderr, " %s=%.1f", names[i], ((i >= 4 && i <= 6) || i == 9) ? (double)v[i] : v[i] / 1e6);
     fprintf(stderr, "\n");
 }
 

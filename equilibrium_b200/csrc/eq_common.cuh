@@ -134,6 +134,14 @@ __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t a) {
 __device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) {
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
+__device__ __forceinline__ void sts_release_cta_u32(uint32_t a, uint32_t v) {
+    asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_acquire_cta_u32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");

@@ -64,9 +64,9 @@
 #define LSX_SLOTS (128 / LSX_CW)                       // the 128-column ring holds this many chunks
 #define LSX_BACK (32 / LSX_CW)                         // after macro step m, chunk m-LSX_BACK is final
 #define LSX_BAR_OFF (LSX_RAW_OFF + 128u * 4u)          // mbarriers: full[], done[], free[], 16 B each
-#define LSX_MISC_OFF (LSX_BAR_OFF + 3u * LSX_SLOTS * 16u)   // [0] ticket broadcast
+#define LSX_MISC_OFF (LSX_BAR_OFF + 3u * LSX_SLOTS * 16u)   // [0] ticket broadcast, [1] chunks whose stores are issued
 #define LSX_SMEM_BYTES (LSX_MISC_OFF + 16u)
-#define LSX_THREADS 96
+#define LSX_THREADS 128
 #define LSX_SPIN_LIMIT (1u << 22)
 
 struct LsxProblem {
@@ -260,9 +260,11 @@ struct LsxJob {
     }
 
     // ------------------------------------------------------------------ STORER warp
+    // Writes finished chunks back and frees their ring slots.  It never fences: the release
+    // (which has to wait until the stores have drained, microseconds under load) is the
+    // PUBLISHER's job, so the ring keeps moving while a release is in flight.
     __device__ __forceinline__ bool run_storer() const {
         float *__restrict__ x = pr.x;
-        unsigned *my_flag = pr.progress + (size_t)k * NB + b;
         float *raw_out = (b + 1 < NB) ? pr.raw + (size_t)(b + 1) * P : nullptr;
         const uint32_t raw_s = sbase + LSX_RAW_OFF;
         constexpr int LPR = LSX_CW / 4, RPP = 32 / LPR;
@@ -270,41 +272,63 @@ struct LsxJob {
         // band rows (tile rows 1..32); the bottom frame row N-1 travels with the last band
         const int t_hi = last_band ? 33 : 32;
         const int t_lo = (ORIENT == EQ_PASSIVE && b == 0) ? 0 : 1;  // Passive rewrites frame row 0
-        int q = 0;
-        while (q < NC) {
+        for (int q = 0; q < NC; ++q) {
             const long long t0 = p.stats ? lsx_clock() : 0;
             if (!lsx_wait_bar(bar_done(q), use_parity(q), p.error, lane)) return false;
             const long long t1 = p.stats ? lsx_clock() : 0;
-            // write back every chunk that is already final (the release below is the expensive part:
-            // it waits for the stores to drain, so it is amortised over as many chunks as are ready)
-            for (;;) {
-                const uint32_t slot = (uint32_t)(q % LSX_SLOTS) * (LSX_CW * 4u);
-                const int col0 = LSX_CW * q;
+            const uint32_t slot = (uint32_t)(q % LSX_SLOTS) * (LSX_CW * 4u);
+            const int col0 = LSX_CW * q;
 #pragma unroll
-                for (int g = 0; g < (LSX_XROWS + RPP - 1) / RPP; ++g) {
-                    const int t = RPP * g + rr;
-                    const int row = j0 - 1 + t;
-                    if (t >= t_lo && t <= t_hi && row <= N - 1) {
-                        const float4 v = lds_f32x4(sbase + LSX_XS_OFF + (uint32_t)t * 512u + slot + 16u * sub);
-                        *reinterpret_cast<float4 *>(x + (size_t)row * P + col0 + 4 * sub) = v;
-                    }
+            for (int g = 0; g < (LSX_XROWS + RPP - 1) / RPP; ++g) {
+                const int t = RPP * g + rr;
+                const int row = j0 - 1 + t;
+                if (t >= t_lo && t <= t_hi && row <= N - 1) {
+                    const float4 v = lds_f32x4(sbase + LSX_XS_OFF + (uint32_t)t * 512u + slot + 16u * sub);
+                    *reinterpret_cast<float4 *>(x + (size_t)row * P + col0 + 4 * sub) = v;
                 }
-                if (raw_out && lane < LSX_CW) raw_out[col0 + lane] = lds_f32(raw_s + (uint32_t)((col0 + lane) & 127) * 4u);
-                __syncwarp();                             // every lane's smem reads of this slot are done
-                if (lane == 0) mbar_arrive(bar_free(q));  // the ring slot may be refilled
-                ++q;
-                if (q >= NC) break;
-                int more = 0;
-                if (lane == 0) more = mbar_test_wait(bar_done(q), use_parity(q)) ? 1 : 0;
-                more = __shfl_sync(0xffffffffu, more, 0);
-                if (!more) break;
             }
-            const long long t2 = p.stats ? lsx_clock() : 0;
-            __syncwarp();
-            if (lane == 0) st_release_u32(my_flag, (unsigned)q);   // the release makes the stores visible GPU-wide
-            if (p.stats) { const long long t3 = lsx_clock(); LSX_STAT(10, t1 - t0); LSX_STAT(11, t2 - t1); LSX_STAT(12, t3 - t2); }
+            if (raw_out && lane < LSX_CW) raw_out[col0 + lane] = lds_f32(raw_s + (uint32_t)((col0 + lane) & 127) * 4u);
+            __syncwarp();                             // every lane's smem reads and global stores are issued
+            if (lane == 0) {
+                mbar_arrive(bar_free(q));             // the ring slot may be refilled
+                sts_release_cta_u32(sbase + LSX_MISC_OFF + 4u, (uint32_t)q + 1u);   // the publisher may release it
+            }
+            if (p.stats) { const long long t2 = lsx_clock(); LSX_STAT(10, t1 - t0); LSX_STAT(11, t2 - t1); }
         }
         return true;
+    }
+
+    // ------------------------------------------------------------------ PUBLISHER warp
+    // One lane: wait until the storer has issued the stores of the next chunk(s), then
+    // st.release the progress counter.  The storer's stores happen-before the release through
+    // the mbarrier (CTA scope) and the release is cumulative, the same pattern as
+    // "__syncthreads(); if (tid == 0) { __threadfence(); flag = 1; }".
+    __device__ __forceinline__ bool run_publisher() const {
+        unsigned *my_flag = pr.progress + (size_t)k * NB + b;
+        const uint32_t cnt = sbase + LSX_MISC_OFF + 4u;
+        int q = 0, ok = 1;
+        while (q < NC && ok) {
+            if (lane == 0) {
+                unsigned spins = 0;
+                int have;
+                while ((have = (int)lds_acquire_cta_u32(cnt)) <= q) {     // chunks whose stores are issued
+                    __nanosleep(20);
+                    if ((++spins & 1023u) == 0) {
+                        if (spins >= LSX_SPIN_LIMIT) { *p.error = 3; ok = 0; break; }
+                        if (ld_volatile_s32(p.error) != 0) { ok = 0; break; }
+                    }
+                }
+                if (ok) {
+                    q = have;                                               // take along everything that is ready
+                    const long long t2 = p.stats ? lsx_clock() : 0;
+                    st_release_u32(my_flag, (unsigned)q);
+                    if (p.stats) { const long long t3 = lsx_clock(); LSX_STAT(12, t3 - t2); LSX_STAT(9, 1); }
+                }
+            }
+            q = __shfl_sync(0xffffffffu, q, 0);
+            ok = __shfl_sync(0xffffffffu, ok, 0);
+        }
+        return ok != 0;
     }
 
     // ------------------------------------------------------------------ COMPUTE warp
@@ -479,7 +503,7 @@ struct LsxJob {
     }
 };
 
-// Three warps per CTA (compute / loader / storer); persistent CTAs pull jobs from the ticket counter.
+// Four warps per CTA (compute / loader / storer / publisher); persistent CTAs pull jobs from the ticket counter.
 __global__ void __launch_bounds__(LSX_THREADS) k_linsolve_exact(const LsxParams p) {
     EQ_DYN_SMEM(lsx_smem_raw);
     const uint32_t sbase = smem_u32(lsx_smem_raw);
@@ -492,6 +516,7 @@ __global__ void __launch_bounds__(LSX_THREADS) k_linsolve_exact(const LsxParams 
         if (threadIdx.x == 0) {
             const unsigned t = (ld_volatile_s32(p.error) != 0) ? 0xffffffffu : atomicAdd(p.ticket, 1u);
             sts_u32(sbase + LSX_MISC_OFF, t);
+            sts_u32(sbase + LSX_MISC_OFF + 4u, 0u);
             for (int i = 0; i < LSX_SLOTS; ++i) {
                 mbar_init(sbase + LSX_BAR_OFF + (uint32_t)i * 16u, 32u);                       // full: 32 loader lanes
                 mbar_init(sbase + LSX_BAR_OFF + (uint32_t)(LSX_SLOTS + i) * 16u, 1u);          // done: compute lane 0
@@ -510,7 +535,8 @@ __global__ void __launch_bounds__(LSX_THREADS) k_linsolve_exact(const LsxParams 
         const LsxJob<O> job(p, pr, sbase, b, k, lane);            \
         if (warp == 0) job.run_compute();                         \
         else if (warp == 1) job.run_loader();                     \
-        else job.run_storer();                                    \
+        else if (warp == 2) job.run_storer();                     \
+        else job.run_publisher();                                 \
     }
         if (pr.orient == EQ_ADJUST_ROW) LSX_DISPATCH(EQ_ADJUST_ROW)
         else if (pr.orient == EQ_ADJUST_COLUMN) LSX_DISPATCH(EQ_ADJUST_COLUMN)

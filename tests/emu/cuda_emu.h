@@ -134,6 +134,8 @@ static inline float4 lds_f32x4(uint32_t a) { float4 v; memcpy(&v, eq_emu::dyn_sm
 static inline void cp_async_16s(uint32_t saddr, const void *gmem) { memcpy(eq_emu::dyn_smem() + saddr, gmem, 16); }
 static inline void sts_u32(uint32_t a, uint32_t v) { memcpy(eq_emu::dyn_smem() + a, &v, 4); }
 static inline uint32_t lds_u32(uint32_t a) { uint32_t v; memcpy(&v, eq_emu::dyn_smem() + a, 4); return v; }
+static inline void sts_release_cta_u32(uint32_t a, uint32_t v) { __atomic_store_n(reinterpret_cast<uint32_t *>(eq_emu::dyn_smem() + a), v, __ATOMIC_RELEASE); }
+static inline uint32_t lds_acquire_cta_u32(uint32_t a) { return __atomic_load_n(reinterpret_cast<uint32_t *>(eq_emu::dyn_smem() + a), __ATOMIC_ACQUIRE); }
 // mbarrier stand-in: 16-byte slot {pending, phase, count}
 struct eq_emu_mbar { std::atomic<uint32_t> pending, phase; uint32_t count, pad; };
 static inline eq_emu_mbar *eq_emu_mb(uint32_t a) { return reinterpret_cast<eq_emu_mbar *>(eq_emu::dyn_smem() + a); }
