@@ -84,6 +84,7 @@ struct eq_fluid {
     size_t flags_words;
     std::map<int, uint32_t *> *job_tables;   // keyed by iterations-per-launch
     int lsx_ctas;
+    unsigned long long *lsx_trace;
     unsigned long long *lsx_stats;   // EQ_LSX_STATS=1: device cycle counters of the wavefront kernel
     // timing / profiling
     cudaEvent_t ev0, ev1;
@@ -284,6 +285,7 @@ static int lin_solve_exact(eq_fluid *h, const LinSolveReq *req, int nreq, int64_
         p.ticket = h->flags;
         p.error = reinterpret_cast<int *>(h->flags + 1);
         p.stats = h->lsx_stats;
+        p.trace = h->lsx_trace;
         // ticket := 0, progress := 0; the sticky error word is left alone
         CU(cudaMemsetAsync(h->flags, 0, sizeof(unsigned), h->stream));
         CU(cudaMemsetAsync(h->flags + 8, 0, (size_t)nreq * prog_words * sizeof(unsigned), h->stream));
@@ -477,6 +479,10 @@ static int alloc_handle(const EqParams *params, eq_fluid **out) {
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_linsolve_exact, LSX_THREADS, LSX_SMEM_BYTES));
     h->lsx_ctas = std::max(1, per_sm) * h->sm_count;
     if (const char *e = getenv("EQ_LSX_CTAS_PER_SM")) h->lsx_ctas = std::max(1, std::min(per_sm, atoi(e))) * h->sm_count;
+    if (getenv("EQ_LSX_TRACE")) {
+        CU(cudaMalloc(&h->lsx_trace, 4 * 8 * 128 * sizeof(unsigned long long)));
+        CU(cudaMemsetAsync(h->lsx_trace, 0, 4 * 8 * 128 * sizeof(unsigned long long), h->stream));
+    }
     if (getenv("EQ_LSX_STATS")) {
         CU(cudaMalloc(&h->lsx_stats, 16 * sizeof(unsigned long long)));
         CU(cudaMemsetAsync(h->lsx_stats, 0, 16 * sizeof(unsigned long long), h->stream));
@@ -549,6 +555,7 @@ int eq_destroy(eq_fluid *h) {
     cudaFree(h->counts);
     cudaFree(h->chunk_flags);
     cudaFree(h->lsx_stats);
+    cudaFree(h->lsx_trace);
     cudaFree(h->row_list);
     cudaFree(h->col_list);
     cudaFree(h->raw[0]);
@@ -708,6 +715,24 @@ int eq_step_n(eq_fluid *h, int64_t n, const EqSource *sources, int64_t n_sources
 }
 
 static void dump_lsx_stats(eq_fluid *h) {
+    if (h->lsx_trace) {
+        static unsigned long long tr[4 * 8 * 128];
+        if (cudaMemcpy(tr, h->lsx_trace, sizeof(tr), cudaMemcpyDeviceToHost) == cudaSuccess) {
+            unsigned long long t0 = ~0ull;
+            for (auto v : tr) if (v && v < t0) t0 = v;
+            const char *ev[8] = {"slot_free", "load_issued", "macro_begin", "macro_end", "done_seen", "stored", "release_begin", "released"};
+            for (int b = 0; b < 4; ++b)
+                for (int e = 0; e < 8; ++e) {
+                    fprintf(stderr, "[trace b=%d %-13s]", b, ev[e]);
+                    for (int q = 0; q < 40; ++q) {
+                        const unsigned long long v = tr[(b * 8 + e) * 128 + q];
+                        if (v) fprintf(stderr, " %6.1f", (v - t0) / 1e3); else fprintf(stderr, "      -");
+                    }
+                    fprintf(stderr, "\n");
+                }
+            cudaMemset(h->lsx_trace, 0, sizeof(tr));
+        }
+    }
     if (!h->lsx_stats) return;
     unsigned long long v[16];
     if (cudaMemcpy(v, h->lsx_stats, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return;

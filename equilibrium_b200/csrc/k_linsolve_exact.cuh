@@ -91,6 +91,7 @@ struct LsxParams {
     unsigned *ticket;
     int *error;
     unsigned long long *stats;   // optional [16] cycle counters (EQ_LSX_STATS=1), see eq_api.cu
+    unsigned long long *trace;   // optional event trace of the first jobs (EQ_LSX_TRACE=1): [4 bands][8 events][128 chunks] ns
 };
 
 #ifdef EQ_HOST_EMU
@@ -98,6 +99,12 @@ static inline long long lsx_clock() { return 0; }
 #else
 __device__ __forceinline__ long long lsx_clock() { return clock64(); }
 #endif
+#ifdef EQ_HOST_EMU
+static inline unsigned long long lsx_gtime() { return 0; }
+#else
+__device__ __forceinline__ unsigned long long lsx_gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#endif
+#define LSX_TRACE(ev, q) do { if (p.trace && lane == 0 && k == 0 && b < 4 && (q) < 128) p.trace[((size_t)b * 8 + (ev)) * 128 + (q)] = lsx_gtime(); } while (0)
 #define LSX_STAT(slot, v) do { if (p.stats && lane == 0) atomicAdd(p.stats + (slot), (unsigned long long)(v)); } while (0)
 
 // ---- waiting primitives: lane 0 waits, the result is broadcast; every loop can be aborted ----
@@ -183,7 +190,7 @@ struct LsxJob {
     enum { MODE_FAST = 0, MODE_CODED = 1, MODE_EDGE = 2 };
     __device__ __forceinline__ int macro_mode(int m) const {
         if (LSX_CW * m - 31 < 2 || LSX_CW * m + LSX_CW - 1 > N - 2) return MODE_EDGE;
-        if (ORIENT == EQ_PASSIVE) return (b == 0 || last_band) ? MODE_CODED : MODE_FAST;
+        if (ORIENT == EQ_PASSIVE) return MODE_FAST;   // the frame rows are blended in by the storer
         unsigned any = 0;
 #pragma unroll
         for (int d = 0; d <= LSX_BACK; ++d) any |= cflags[m - d];     // codes are read in chunks m-BACK .. m
@@ -213,6 +220,7 @@ struct LsxJob {
             // the ring slot must have been written back (chunk q-SLOTS) ...
             if (q >= LSX_SLOTS && !lsx_wait_bar(bar_free(q), use_parity(q - LSX_SLOTS), p.error, lane)) return false;
             const long long t1 = p.stats ? lsx_clock() : 0;
+            LSX_TRACE(0, q);
             // ... and the producers of this chunk must have published it
             if (!lsx_wait_flags(flag_prev_iter, (unsigned)q + 1u, flag_band_above, (unsigned)q + 1u, p.error, lane))
                 return false;
@@ -254,6 +262,7 @@ struct LsxJob {
                     }
                 }
             }
+            LSX_TRACE(1, q);
             cp_async_mbar_arrive_noinc(bar_full(q));     // fires when this lane's copies have landed
         }
         return true;
@@ -276,6 +285,7 @@ struct LsxJob {
             const long long t0 = p.stats ? lsx_clock() : 0;
             if (!lsx_wait_bar(bar_done(q), use_parity(q), p.error, lane)) return false;
             const long long t1 = p.stats ? lsx_clock() : 0;
+            LSX_TRACE(4, q);
             const uint32_t slot = (uint32_t)(q % LSX_SLOTS) * (LSX_CW * 4u);
             const int col0 = LSX_CW * q;
 #pragma unroll
@@ -283,7 +293,21 @@ struct LsxJob {
                 const int t = RPP * g + rr;
                 const int row = j0 - 1 + t;
                 if (t >= t_lo && t <= t_hi && row <= N - 1) {
-                    const float4 v = lds_f32x4(sbase + LSX_XS_OFF + (uint32_t)t * 512u + slot + 16u * sub);
+                    float4 v = lds_f32x4(sbase + LSX_XS_OFF + (uint32_t)t * 512u + slot + 16u * sub);
+                    if (ORIENT == EQ_PASSIVE && (row == 0 || row == N - 1)) {
+                        // Passive frame rows (fluid.rs:182-183): x[i,0] = x[i,1], x[i,N-1] = x[i,N-2] for the
+                        // columns 1..N-2 that contain a NoWall cell (quirk Q6; col_fluid is staged in row 0
+                        // of the code tile); interior rows are never changed by the Passive pass, so the
+                        // neighbour row of the tile already holds the value to copy.
+                        const int tn = (row == 0) ? t + 1 : t - 1;
+                        const float4 nb = lds_f32x4(sbase + LSX_XS_OFF + (uint32_t)tn * 512u + slot + 16u * sub);
+                        const uint32_t cf4 = lds_u32(sbase + LSX_CS_OFF + (uint32_t)(q % LSX_SLOTS) * LSX_CW + 4u * sub);
+                        const int c0 = col0 + 4 * sub;
+                        if ((cf4 & 0xffu) && c0 >= 1 && c0 <= N - 2) v.x = nb.x;
+                        if ((cf4 & 0xff00u) && c0 + 1 >= 1 && c0 + 1 <= N - 2) v.y = nb.y;
+                        if ((cf4 & 0xff0000u) && c0 + 2 >= 1 && c0 + 2 <= N - 2) v.z = nb.z;
+                        if ((cf4 & 0xff000000u) && c0 + 3 >= 1 && c0 + 3 <= N - 2) v.w = nb.w;
+                    }
                     *reinterpret_cast<float4 *>(x + (size_t)row * P + col0 + 4 * sub) = v;
                 }
             }
@@ -293,6 +317,7 @@ struct LsxJob {
                 mbar_arrive(bar_free(q));             // the ring slot may be refilled
                 sts_release_cta_u32(sbase + LSX_MISC_OFF + 4u, (uint32_t)q + 1u);   // the publisher may release it
             }
+            LSX_TRACE(5, q);
             if (p.stats) { const long long t2 = lsx_clock(); LSX_STAT(10, t1 - t0); LSX_STAT(11, t2 - t1); }
         }
         return true;
@@ -321,7 +346,9 @@ struct LsxJob {
                 if (ok) {
                     q = have;                                               // take along everything that is ready
                     const long long t2 = p.stats ? lsx_clock() : 0;
+                    LSX_TRACE(6, q - 1);
                     st_release_u32(my_flag, (unsigned)q);
+                    LSX_TRACE(7, q - 1);
                     if (p.stats) { const long long t3 = lsx_clock(); LSX_STAT(12, t3 - t2); LSX_STAT(9, 1); }
                 }
             }
@@ -356,137 +383,89 @@ struct LsxJob {
             const long long tw0 = p.stats ? lsx_clock() : 0;
             if (m + 1 < NC && !lsx_wait_bar(bar_full(m + 1), use_parity(m + 1), p.error, lane)) return false;
             const long long tw1 = p.stats ? lsx_clock() : 0;
+            LSX_TRACE(2, m);
 
             const int mode = macro_mode(m);
-            if (mode != MODE_EDGE) {
-                // ---- interior columns: every lane computes and finalises an interior cell ---------
+            if (mode == MODE_FAST) {
+                // ---- fast loop: every lane on an interior column, nothing to fix up.  Operands of
+                // step t+1 are fetched before the arithmetic of step t (they are not written by
+                // anyone before step t+3), so only SHFL -> 4 FP ops remain on the step-to-step chain.
                 uint32_t o = ((uint32_t)(LSX_CW * m - lane) & 127u) << 2;  // byte offset of column c
                 uint32_t om1 = (o - 4u) & 508u;                            // column c-1
-                if (mode == MODE_FAST) {
-#pragma unroll 4
-                    for (int t = 0; t < LSX_CW; ++t) {
-                        const uint32_t o1 = (o + 4u) & 508u;
-                        float up = __shfl_up_sync(0xffffffffu, cur, 1);
-                        const float right = lds_f32(xs_row + o1);
-                        const float down = lds_f32(xs_row + 512u + o);
-                        const float x0v = lds_f32(x0_row + o);
-                        if (lane == 0) up = lds_f32(xs_top + o);
-                        const float newv = gs_update(x0v, right, cur, down, up, a, c_recip);
-                        if (in_row) sts_f32(xs_row + om1, cur);                // column c-1 is final: F = R
-                        if (lane == 31) sts_f32(raw_s + o, newv);
-                        prev2 = cur;
-                        prev_up = up;
-                        cur = newv;
-                        om1 = o;
-                        o = o1;
-                        __syncwarp();
-                    }
-                } else {
-                    int c = LSX_CW * m - lane;
-#pragma unroll 2
-                    for (int t = 0; t < LSX_CW; ++t, ++c) {
-                        const uint32_t o1 = (o + 4u) & 508u;
-                        float up = __shfl_up_sync(0xffffffffu, cur, 1);
-                        const float right = lds_f32(xs_row + o1);
-                        const float down = lds_f32(xs_row + 512u + o);
-                        const float x0v = lds_f32(x0_row + o);
-                        if (lane == 0) up = lds_f32(xs_top + o);
-                        float newv = gs_update(x0v, right, cur, down, up, a, c_recip);
-                        float F = cur;                                         // R_k(c-1, j)
-                        if (ORIENT == EQ_ADJUST_ROW) {
-                            const unsigned code = lds_u8(cs_row + (om1 >> 2)) & 3u;
-                            F = (code == EQ_CODE_ROW_RIGHT) ? -newv : ((code == EQ_CODE_ROW_LEFT) ? -prev2 : cur);
-                        } else if (ORIENT == EQ_ADJUST_COLUMN) {
-                            if (!in_row) newv = lds_f32(xs_row + o);           // frame row N-1 passes through
-                            const float dn = __shfl_down_sync(0xffffffffu, newv, 1);
-                            const unsigned code = lds_u8(cs_row + (om1 >> 2)) & 12u;
-                            if (code == EQ_CODE_COL_UP) F = -prev_up;
-                            else if (code == EQ_CODE_COL_DOWN) {
-                                if (lane < 31) F = -dn;
-                                else if (last_band) F = -lds_f32(xs_top + 33u * 512u + om1);
-                                // else: the band below patches this cell
-                            }
-                            if (lane == 0 && b > 0) {
-                                // cell (c, j0-1) of the band above takes -R_k(c, j0) when its code says DOWN
-                                const unsigned code0 = lds_u8(cs_top + (o >> 2)) & 12u;
-                                if (code0 == EQ_CODE_COL_DOWN) x[(size_t)(j0 - 1) * P + c] = -newv;
-                            }
-                        } else {
-                            // Passive band that owns a frame row (fluid.rs:182-183, conditional per Q6)
-                            if ((j == 1 || j == N - 2) && lds_u8(cs_top + (om1 >> 2))) {
-                                if (j == 1) sts_f32(xs_top + om1, cur);
-                                if (j == N - 2) sts_f32(xs_row + 512u + om1, cur);
-                            }
-                        }
-                        if (in_row) sts_f32(xs_row + om1, F);
-                        if (lane == 31 && in_row) sts_f32(raw_s + o, newv);
-                        prev2 = cur;
-                        prev_up = up;
-                        cur = newv;
-                        om1 = o;
-                        o = o1;
-                        __syncwarp();
-                    }
+                float right = lds_f32(xs_row + ((o + 4u) & 508u));
+                float down = lds_f32(xs_row + 512u + o);
+                float x0v = lds_f32(x0_row + o);
+                float topv = (lane == 0) ? lds_f32(xs_top + o) : 0.f;
+#pragma unroll
+                for (int t = 0; t < LSX_CW; ++t) {
+                    const uint32_t o1 = (o + 4u) & 508u, o2 = (o + 8u) & 508u;
+                    float up = __shfl_up_sync(0xffffffffu, cur, 1);
+                    if (lane == 0) up = topv;
+                    const float right_n = lds_f32(xs_row + o2);
+                    const float down_n = lds_f32(xs_row + 512u + o1);
+                    const float x0_n = lds_f32(x0_row + o1);
+                    if (lane == 0) topv = lds_f32(xs_top + o1);
+                    const float newv = gs_update(x0v, right, cur, down, up, a, c_recip);
+                    if (in_row) sts_f32(xs_row + om1, cur);                // column c-1 is final: F = R
+                    if (lane == 31) sts_f32(raw_s + o, newv);
+                    prev2 = cur;
+                    prev_up = up;
+                    cur = newv;
+                    om1 = o;
+                    o = o1;
+                    right = right_n;
+                    down = down_n;
+                    x0v = x0_n;
+                    __syncwarp();
                 }
             } else {
-                // ---- general loop: frame columns, fix-ups, Passive frame copies ----------------------
+                // ---- general loop, written with selects instead of branches: every shared-memory
+                // address is valid for any column (the ring wraps), so operands are loaded
+                // unconditionally and the column-range tests only pick results.  MODE_CODED skips
+                // the range tests (every lane is on an interior column).
+                const bool ranged = (mode == MODE_EDGE);
                 const int s_end = min(LSX_CW * m + LSX_CW, S);
                 for (int s = LSX_CW * m; s < s_end; ++s) {
                     const int c = s - lane;          // column this lane computes now (0 = left frame cell)
+                    const int cf = c - 1;            // column finalised now
                     const uint32_t o = ((uint32_t)c & 127u) << 2;
                     const uint32_t om1 = (o - 4u) & 508u;
                     const float up = __shfl_up_sync(0xffffffffu, cur, 1);
-                    float newv = cur;
-                    float top = up;
-                    if (c >= 0 && c <= N - 1) {
-                        if (in_row && c >= 1 && c <= N - 2) {
-                            const float right = lds_f32(xs_row + ((o + 4u) & 508u));
-                            const float down = lds_f32(xs_row + 512u + o);
-                            if (lane == 0) top = lds_f32(xs_top + o);
-                            const float x0v = lds_f32(x0_row + o);
-                            newv = gs_update(x0v, right, cur, down, top, a, c_recip);
-                        } else if (in_row || ORIENT == EQ_ADJUST_COLUMN) {
-                            newv = lds_f32(xs_row + o);      // frame column / frame row N-1: pass through
-                        }
-                    }
-                    float dn = 0.f;
-                    if (ORIENT == EQ_ADJUST_COLUMN) dn = __shfl_down_sync(0xffffffffu, newv, 1);
-                    const int cf = c - 1;            // column finalised now
-                    if (in_row && cf >= 1 && cf <= N - 2) {
-                        float F = cur;               // R_k(cf, j)
-                        if (ORIENT == EQ_ADJUST_ROW) {
-                            const unsigned code = lds_u8(cs_row + (om1 >> 2)) & 3u;
-                            if (code == EQ_CODE_ROW_RIGHT) F = -newv;
-                            else if (code == EQ_CODE_ROW_LEFT) F = -prev2;
-                        } else if (ORIENT == EQ_ADJUST_COLUMN) {
-                            const unsigned code = lds_u8(cs_row + (om1 >> 2)) & 12u;
-                            if (code == EQ_CODE_COL_UP) F = -prev_up;
-                            else if (code == EQ_CODE_COL_DOWN) {
-                                if (lane < 31) F = -dn;
-                                else if (last_band) F = -lds_f32(xs_top + 33u * 512u + om1);
-                                // else: the band below patches this cell (see below)
-                            }
-                        }
-                        sts_f32(xs_row + om1, F);
-                        if (ORIENT == EQ_PASSIVE) {   // fluid.rs:179-187, conditional per quirk Q6
-                            if (row_has_fluid) {
-                                if (cf == 1) sts_f32(xs_row, cur);
-                                if (cf == N - 2) sts_f32(xs_row + (((uint32_t)(N - 1) & 127u) << 2), cur);
-                            }
-                            if ((j == 1 || j == N - 2) && lds_u8(cs_top + (om1 >> 2))) {
-                                if (j == 1) sts_f32(xs_top + om1, cur);
-                                if (j == N - 2) sts_f32(xs_row + 512u + om1, cur);
-                            }
-                        }
-                    }
-                    if (in_row && c >= 1 && c <= N - 2) {
-                        if (ORIENT == EQ_ADJUST_COLUMN && lane == 0 && b > 0) {
+                    const float right = lds_f32(xs_row + ((o + 4u) & 508u));
+                    const float down = lds_f32(xs_row + 512u + o);
+                    const float x0v = lds_f32(x0_row + o);
+                    const float self = lds_f32(xs_row + o);
+                    const float top = (lane == 0) ? lds_f32(xs_top + o) : up;
+                    const bool gs_ok = in_row && (!ranged || (c >= 1 && c <= N - 2));
+                    const bool pass_ok = (!ranged || (c >= 0 && c <= N - 1)) && (in_row || ORIENT == EQ_ADJUST_COLUMN);
+                    const float g = gs_update(x0v, right, cur, down, top, a, c_recip);
+                    const float newv = gs_ok ? g : (pass_ok ? self : cur);   // frame cells pass through
+                    const bool fin = in_row && (!ranged || (cf >= 1 && cf <= N - 2));
+                    float F = cur;                   // R_k(cf, j)
+                    if (ORIENT == EQ_ADJUST_ROW) {
+                        const unsigned code = lds_u8(cs_row + (om1 >> 2)) & 3u;
+                        F = (code == EQ_CODE_ROW_RIGHT) ? -newv : ((code == EQ_CODE_ROW_LEFT) ? -prev2 : cur);
+                    } else if (ORIENT == EQ_ADJUST_COLUMN) {
+                        const float dn = __shfl_down_sync(0xffffffffu, newv, 1);
+                        const unsigned code = lds_u8(cs_row + (om1 >> 2)) & 12u;
+                        const float below = (lane < 31) ? dn : lds_f32(xs_top + 33u * 512u + om1);
+                        // a DOWN cell in lane 31 of a band that is not the last one is patched by the band below
+                        const bool take_down = (code == EQ_CODE_COL_DOWN) && (lane < 31 || last_band);
+                        F = (code == EQ_CODE_COL_UP) ? -prev_up : (take_down ? -below : cur);
+                        if (gs_ok && lane == 0 && b > 0) {
                             // cell (c, j0-1) of the band above takes -R_k(c, j0) when its code says DOWN
                             const unsigned code0 = lds_u8(cs_top + (o >> 2)) & 12u;
                             if (code0 == EQ_CODE_COL_DOWN) x[(size_t)(j0 - 1) * P + c] = -newv;
                         }
-                        if (lane == 31) sts_f32(raw_s + o, newv);
                     }
+                    if (fin) sts_f32(xs_row + om1, F);
+                    if (ORIENT == EQ_PASSIVE && ranged && fin && row_has_fluid) {
+                        // x[0,j] = x[1,j], x[N-1,j] = x[N-2,j] (fluid.rs:185-186, conditional per quirk Q6);
+                        // the frame ROWS are blended in by the storer
+                        if (cf == 1) sts_f32(xs_row, cur);
+                        if (cf == N - 2) sts_f32(xs_row + (((uint32_t)(N - 1) & 127u) << 2), cur);
+                    }
+                    if (gs_ok && lane == 31) sts_f32(raw_s + o, newv);
                     prev2 = cur;
                     prev_up = top;
                     cur = newv;
@@ -495,6 +474,7 @@ struct LsxJob {
             }
             // every lane has finalised the columns below CW*(m+1)-32: hand that chunk to the storer
             if (m >= LSX_BACK && m - LSX_BACK < NC && lane == 0) mbar_arrive(bar_done(m - LSX_BACK));
+            LSX_TRACE(3, m);
             if (p.stats) { const long long tw2 = lsx_clock(); LSX_STAT(0, tw1 - tw0); LSX_STAT(1 + mode, tw2 - tw1); LSX_STAT(4 + mode, 1); }
         }
         if (lane == 0)
