@@ -85,6 +85,8 @@ struct eq_fluid {
     std::map<int, uint32_t *> *job_tables;   // keyed by iterations-per-launch
     int lsx_ctas;
     unsigned long long *lsx_trace;
+    unsigned long long *lsx_jobtimes;
+    size_t lsx_jobtimes_n;
     unsigned long long *lsx_stats;   // EQ_LSX_STATS=1: device cycle counters of the wavefront kernel
     // timing / profiling
     cudaEvent_t ev0, ev1;
@@ -285,7 +287,20 @@ static int lin_solve_exact(eq_fluid *h, const LinSolveReq *req, int nreq, int64_
         p.ticket = h->flags;
         p.error = reinterpret_cast<int *>(h->flags + 1);
         p.stats = h->lsx_stats;
+        p.debug_nodeps = getenv("EQ_LSX_NODEPS") ? 1 : 0;
+        p.slack = getenv("EQ_LSX_SLACK") ? atoi(getenv("EQ_LSX_SLACK")) : 0;
         p.trace = h->lsx_trace;
+        p.jobtimes = nullptr;
+        if (getenv("EQ_LSX_JOBTIMES")) {
+            const size_t n = 2 * (size_t)kc * NB * nreq;
+            if (h->lsx_jobtimes_n < n) {
+                cudaFree(h->lsx_jobtimes);
+                CU(cudaMalloc(&h->lsx_jobtimes, n * sizeof(unsigned long long)));
+                h->lsx_jobtimes_n = n;
+            }
+            CU(cudaMemsetAsync(h->lsx_jobtimes, 0, n * sizeof(unsigned long long), h->stream));
+            p.jobtimes = h->lsx_jobtimes;
+        }
         // ticket := 0, progress := 0; the sticky error word is left alone
         CU(cudaMemsetAsync(h->flags, 0, sizeof(unsigned), h->stream));
         CU(cudaMemsetAsync(h->flags + 8, 0, (size_t)nreq * prog_words * sizeof(unsigned), h->stream));
@@ -556,6 +571,7 @@ int eq_destroy(eq_fluid *h) {
     cudaFree(h->chunk_flags);
     cudaFree(h->lsx_stats);
     cudaFree(h->lsx_trace);
+    cudaFree(h->lsx_jobtimes);
     cudaFree(h->row_list);
     cudaFree(h->col_list);
     cudaFree(h->raw[0]);
@@ -715,6 +731,15 @@ int eq_step_n(eq_fluid *h, int64_t n, const EqSource *sources, int64_t n_sources
 }
 
 static void dump_lsx_stats(eq_fluid *h) {
+    if (h->lsx_jobtimes && h->lsx_jobtimes_n) {
+        std::vector<unsigned long long> v(h->lsx_jobtimes_n);
+        if (cudaMemcpy(v.data(), h->lsx_jobtimes, v.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess) {
+            if (FILE *f = fopen(getenv("EQ_LSX_JOBTIMES"), "wb")) {
+                fwrite(v.data(), sizeof(unsigned long long), v.size(), f);
+                fclose(f);
+            }
+        }
+    }
     if (h->lsx_trace) {
         static unsigned long long tr[4 * 8 * 128];
         if (cudaMemcpy(tr, h->lsx_trace, sizeof(tr), cudaMemcpyDeviceToHost) == cudaSuccess) {

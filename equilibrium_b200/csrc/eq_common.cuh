@@ -101,6 +101,8 @@ __device__ __forceinline__ float4 lds_f32x4(uint32_t a) {
 __device__ __forceinline__ void cp_async_16s(uint32_t saddr, const void *gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(gmem) : "memory");
 }
+// pull a line into L2 ahead of time (no register, no shared memory)
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // mbarrier (shared::cta) -- each barrier gets a 16-byte slot (8 used on the device)
 __device__ __forceinline__ void mbar_init(uint32_t a, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");

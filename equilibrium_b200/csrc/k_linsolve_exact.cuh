@@ -67,6 +67,7 @@
 #define LSX_MISC_OFF (LSX_BAR_OFF + 3u * LSX_SLOTS * 16u)   // [0] ticket broadcast, [1] chunks whose stores are issued
 #define LSX_SMEM_BYTES (LSX_MISC_OFF + 16u)
 #define LSX_THREADS 128
+#define LSX_PF 24                                      // L2 prefetch distance of the loader, in chunks
 #define LSX_SPIN_LIMIT (1u << 22)
 
 struct LsxProblem {
@@ -90,7 +91,10 @@ struct LsxParams {
     int N, P, K, NB, NC;
     unsigned *ticket;
     int *error;
+    int slack;                   // a consumer asks its producers to be this many chunks further ahead than strictly needed
+    int debug_nodeps;            // EQ_LSX_NODEPS=1: skip the dependency waits (WRONG results; throughput experiments only)
     unsigned long long *stats;   // optional [16] cycle counters (EQ_LSX_STATS=1), see eq_api.cu
+    unsigned long long *jobtimes; // optional [2 * njobs * nprob] start/end ns of every job (EQ_LSX_JOBTIMES=1)
     unsigned long long *trace;   // optional event trace of the first jobs (EQ_LSX_TRACE=1): [4 bands][8 events][128 chunks] ns
 };
 
@@ -104,7 +108,7 @@ static inline unsigned long long lsx_gtime() { return 0; }
 #else
 __device__ __forceinline__ unsigned long long lsx_gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #endif
-#define LSX_TRACE(ev, q) do { if (p.trace && lane == 0 && k == 0 && b < 4 && (q) < 128) p.trace[((size_t)b * 8 + (ev)) * 128 + (q)] = lsx_gtime(); } while (0)
+#define LSX_TRACE(ev, q) do { if (p.trace && lane == 0 && k == p.K - 1 && (b < 3 || b == p.NB - 1) && (q) >= 200 && (q) < 328) p.trace[((size_t)(b < 3 ? b : 3) * 8 + (ev)) * 128 + (q) - 200] = lsx_gtime(); } while (0)
 #define LSX_STAT(slot, v) do { if (p.stats && lane == 0) atomicAdd(p.stats + (slot), (unsigned long long)(v)); } while (0)
 
 // ---- waiting primitives: lane 0 waits, the result is broadcast; every loop can be aborted ----
@@ -114,8 +118,11 @@ __device__ __forceinline__ bool lsx_wait_flags(const unsigned *f1, unsigned n1, 
     int ok = 1;
     if (lane == 0) {
         unsigned spins = 0;
-        while ((f1 && ld_acquire_u32(f1) < n1) || (f2 && ld_acquire_u32(f2) < n2)) {
-            __nanosleep(32);
+        // spin with relaxed loads (an acquire load is followed by an L1 invalidate, CCTL.IVALL, which
+        // the five loaders of an SM would otherwise issue every few hundred cycles), then take one
+        // acquire load of the flag that was seen set: it reads from the release and synchronises.
+        while ((f1 && ld_relaxed_u32(f1) < n1) || (f2 && ld_relaxed_u32(f2) < n2)) {
+            __nanosleep(64);
             if ((++spins & 1023u) == 0) {
                 if (spins >= LSX_SPIN_LIMIT) {
                     *error = 1;
@@ -127,6 +134,10 @@ __device__ __forceinline__ bool lsx_wait_flags(const unsigned *f1, unsigned n1, 
                     break;
                 }
             }
+        }
+        if (ok) {
+            if (f1) (void)ld_acquire_u32(f1);
+            if (f2) (void)ld_acquire_u32(f2);
         }
     }
     ok = __shfl_sync(0xffffffffu, ok, 0);
@@ -216,13 +227,21 @@ struct LsxJob {
         constexpr int RPP = 32 / LPR;              // rows per pass
         const int sub = lane % LPR, rr = lane / LPR;
         for (int q = 0; q < NC; ++q) {
+            // x0 is re-read from HBM every iteration and has no dependency: pull the chunk that will be
+            // staged LSX_PF chunks from now into L2, one row per lane (in iteration 0 x is cold as well)
+            if (q + LSX_PF < NC) {
+                prefetch_l2(x0 + (size_t)(j0 + lane) * P + LSX_CW * (q + LSX_PF));
+                if (k == 0) prefetch_l2(x + (size_t)(j0 + lane) * P + LSX_CW * (q + LSX_PF));
+            }
             const long long t0 = p.stats ? lsx_clock() : 0;
             // the ring slot must have been written back (chunk q-SLOTS) ...
             if (q >= LSX_SLOTS && !lsx_wait_bar(bar_free(q), use_parity(q - LSX_SLOTS), p.error, lane)) return false;
             const long long t1 = p.stats ? lsx_clock() : 0;
             LSX_TRACE(0, q);
             // ... and the producers of this chunk must have published it
-            if (!lsx_wait_flags(flag_prev_iter, (unsigned)q + 1u, flag_band_above, (unsigned)q + 1u, p.error, lane))
+            if (!p.debug_nodeps &&
+                !lsx_wait_flags(flag_prev_iter, (unsigned)min(q + 1 + p.slack, NC), flag_band_above,
+                                (unsigned)min(q + 1 + p.slack, NC), p.error, lane))
                 return false;
             if (p.stats) { const long long t2 = lsx_clock(); LSX_STAT(7, t1 - t0); LSX_STAT(8, t2 - t1); }
             const uint32_t slot = (uint32_t)(q % LSX_SLOTS) * (LSX_CW * 4u);   // byte offset of the chunk in a 512 B row
@@ -337,7 +356,7 @@ struct LsxJob {
                 unsigned spins = 0;
                 int have;
                 while ((have = (int)lds_acquire_cta_u32(cnt)) <= q) {     // chunks whose stores are issued
-                    __nanosleep(20);
+                    __nanosleep(64);
                     if ((++spins & 1023u) == 0) {
                         if (spins >= LSX_SPIN_LIMIT) { *p.error = 3; ok = 0; break; }
                         if (ld_volatile_s32(p.error) != 0) { ok = 0; break; }
@@ -510,6 +529,7 @@ __global__ void __launch_bounds__(LSX_THREADS) k_linsolve_exact(const LsxParams 
         const uint32_t jb = p.jobs[t / (unsigned)p.nprob];
         const int k = (int)(jb >> 16), b = (int)(jb & 0xffffu);
         const LsxProblem &pr = p.prob[pi];
+        if (p.jobtimes && threadIdx.x == 0) p.jobtimes[2 * ((size_t)(k * p.NB + b) * p.nprob + pi)] = lsx_gtime();
 #define LSX_DISPATCH(O)                                           \
     {                                                             \
         const LsxJob<O> job(p, pr, sbase, b, k, lane);            \
@@ -522,6 +542,7 @@ __global__ void __launch_bounds__(LSX_THREADS) k_linsolve_exact(const LsxParams 
         else if (pr.orient == EQ_ADJUST_COLUMN) LSX_DISPATCH(EQ_ADJUST_COLUMN)
         else LSX_DISPATCH(EQ_PASSIVE)
 #undef LSX_DISPATCH
+        if (p.jobtimes && threadIdx.x == 0) p.jobtimes[2 * ((size_t)(k * p.NB + b) * p.nprob + pi) + 1] = lsx_gtime();
         // a role that gave up has set *p.error (or seen it set); the next pass of the loop makes
         // thread 0 read it and every thread leaves together
     }

@@ -157,6 +157,7 @@ static inline bool mbar_try_wait(uint32_t a, uint32_t parity) {
 }
 static inline bool mbar_test_wait(uint32_t a, uint32_t parity) { return (eq_emu_mb(a)->phase.load(std::memory_order_acquire) & 1u) != parity; }
 static inline void cp_async_mbar_arrive_noinc(uint32_t a) { mbar_arrive(a); }
+static inline void prefetch_l2(const void *) {}
 static inline void cp_async_commit() {}
 template <int N>
 static inline void cp_async_wait() {}
