@@ -3,9 +3,9 @@
 reference's own `Fluid` API.  Importing this package does not load the native
 library; creating a `Fluid` does, and fails loudly if it is missing."""
 from .configs import FluidConfigs, SimulationConfigs
-from .fluid import ContainerWall, Fluid
+from .fluid import ContainerWall, Fluid, connect_distributed, connect_local
 from .obstacle import ObstaclesType, Rectangle
 from ._lib import EquilibriumError
 
 __all__ = ["Fluid", "FluidConfigs", "SimulationConfigs", "Rectangle", "ObstaclesType",
-           "ContainerWall", "EquilibriumError"]
+           "ContainerWall", "EquilibriumError", "connect_local", "connect_distributed"]

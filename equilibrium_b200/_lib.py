@@ -103,7 +103,9 @@ SIGNATURES = {
     "eq_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "eq_host_free": (C.c_int, [C.c_void_p]),
     "eq_l2_flush": (C.c_int, [_H]),
-    "eq_comm_unique_id": (C.c_int, [C.POINTER(C.c_uint8)]),
+    "eq_ipc_blob_bytes": (C.c_int, []),
+    "eq_ipc_export": (C.c_int, [_H, C.c_void_p, C.c_size_t]),
+    "eq_ipc_attach": (C.c_int, [_H, C.c_void_p, C.c_size_t, C.c_int]),
 }
 
 _cache: dict[str, C.CDLL] = {}

@@ -17,6 +17,9 @@
 #include "k_linsolve_exact.cuh"
 #include "k_linsolve_rb.cuh"
 #include "k_stencils.cuh"
+#include "k_multigpu.cuh"
+
+#include <unistd.h>
 
 // ---------------------------------------------------------------------------
 // errors
@@ -99,6 +102,17 @@ struct eq_fluid {
     int64_t prof_steps;
     void *l2buf;
     size_t l2bytes;
+    // row slabs over several GPUs (one process per GPU, or several handles in one process)
+    int rank, world;
+    int b_lo, b_hi;                              // owned bands of the wavefront solver
+    float *peer_f[EQ_MAX_RANKS][6];              // every rank's fields / raw streams / flags / sync slots
+    float *peer_raw[EQ_MAX_RANKS][2];
+    unsigned *peer_flags[EQ_MAX_RANKS];
+    unsigned *peer_sync[EQ_MAX_RANKS];
+    bool peer_ipc[EQ_MAX_RANKS];                 // mapped with cudaIpcOpenMemHandle (must be closed)
+    unsigned *sync;                              // my cross-GPU sync slots
+    unsigned halo_epoch, bar_epoch;
+    bool attached;
 };
 
 static size_t field_elems(const eq_fluid *h) { return (size_t)h->L.P * h->L.rows; }
@@ -152,6 +166,78 @@ static int prof_collect(eq_fluid *h) {
 static inline dim3 row_grid(const eq_fluid *h, int rows, int threads = 256) {
     return dim3((unsigned)((h->L.N + threads - 1) / threads), (unsigned)rows, 1);
 }
+static int check_launch(const char *what);
+// rows of the interior (1..N-2) that this rank owns
+static inline int owned_interior_rows(const eq_fluid *h) {
+    return std::min(h->L.row1, h->L.N - 1) - std::max(h->L.row0, 1);
+}
+
+// ---------------------------------------------------------------------------
+// multi-GPU plumbing: halo rows and barriers (k_multigpu.cuh)
+// ---------------------------------------------------------------------------
+static int field_index(const eq_fluid *h, const float *f) {
+    for (int i = 0; i < 6; ++i)
+        if (h->f[i] == f) return i;
+    return -1;
+}
+
+static int need_attached(eq_fluid *h) {
+    if (h->world > 1 && !h->attached)
+        return eq_fail(EQ_ERR_STATE, "multi-GPU handle used before eq_ipc_attach (rank %d of %d)", h->rank, h->world);
+    return EQ_OK;
+}
+
+// refresh the ghost rows of `field` on both neighbours and mine from theirs
+static int halo_xchg(eq_fluid *h, float *field) {
+    if (h->world <= 1) return EQ_OK;
+    TRY(need_attached(h));
+    const int fi = field_index(h, field);
+    if (fi < 0) return eq_fail(EQ_ERR_INVALID, "halo exchange of an unknown field");
+    ProfScope ps(h, CAT_OTHER, 1);
+    EqHaloArgs a;
+    memset(&a, 0, sizeof(a));
+    a.field = field;
+    a.peer_up = h->rank > 0 ? h->peer_f[h->rank - 1][fi] : nullptr;
+    a.peer_down = h->rank + 1 < h->world ? h->peer_f[h->rank + 1][fi] : nullptr;
+    a.sync = h->sync;
+    a.sync_up = h->rank > 0 ? h->peer_sync[h->rank - 1] : nullptr;
+    a.sync_down = h->rank + 1 < h->world ? h->peer_sync[h->rank + 1] : nullptr;
+    a.epoch = ++h->halo_epoch;
+    a.error = reinterpret_cast<int *>(h->flags + 1);
+    EQ_LAUNCH(k_halo_exchange, 2, 1024, 16, h->stream, a, h->L);
+    return check_launch("k_halo_exchange");
+}
+
+// every rank has finished what it launched so far
+static int barrier_all(eq_fluid *h) {
+    if (h->world <= 1) return EQ_OK;
+    TRY(need_attached(h));
+    ProfScope ps(h, CAT_OTHER, 1);
+    EqBarrierArgs a;
+    memset(&a, 0, sizeof(a));
+    a.sync = h->sync;
+    for (int r = 0; r < h->world; ++r) a.peer_sync[r] = h->peer_sync[r];
+    a.rank = h->rank;
+    a.world = h->world;
+    a.epoch = ++h->bar_epoch;
+    a.error = reinterpret_cast<int *>(h->flags + 1);
+    EQ_LAUNCH(k_barrier_all, 1, 32, 0, h->stream, a);
+    return check_launch("k_barrier_all");
+}
+
+static EqPeerTable peer_table(const eq_fluid *h, const float *field) {
+    EqPeerTable t;
+    memset(&t, 0, sizeof(t));
+    t.world = std::max(1, h->world);
+    const int fi = field ? field_index(h, field) : -1;
+    const int NB = (h->L.N - 2 + 31) / 32;
+    for (int r = 0; r < t.world; ++r) {
+        t.base[r] = (h->world > 1 && fi >= 0) ? h->peer_f[r][fi] : field;
+        t.row_begin[r] = (r == 0) ? 0 : 1 + 32 * (int)((int64_t)r * NB / t.world);
+    }
+    t.row_begin[t.world] = h->L.N;
+    return t;
+}
 
 static int check_launch(const char *what) {
     cudaError_t e = cudaGetLastError();
@@ -202,6 +288,7 @@ static int ensure_tables(eq_fluid *h) {
 // ---------------------------------------------------------------------------
 static int set_boundaries(eq_fluid *h, int orient, float *x) {
     TRY(ensure_tables(h));
+    if (orient == EQ_ADJUST_COLUMN) TRY(halo_xchg(h, x));   // the mirrored wall cell may sit in a ghost row
     ProfScope ps(h, CAT_BND, 1);
     const EqLayout L = h->L;
     if (orient == EQ_PASSIVE) {
@@ -235,12 +322,14 @@ static int get_job_table(eq_fluid *h, int kc, const uint32_t **out) {
     }
     const int NB = (h->L.N - 2 + 31) / 32;
     std::vector<uint32_t> tab;
-    tab.reserve((size_t)kc * NB);
-    // wavefront order: w = b + 2k ascending; a job depends only on w-1
+    tab.reserve((size_t)kc * (h->b_hi - h->b_lo));
+    // wavefront order: w = b + 2k ascending; a job depends only on w-1.  A rank lists
+    // only the bands of its slab; every rank uses the same global order, so cross-GPU waits also
+    // point at jobs that were handed out earlier on their own GPU.
     for (int w = 0; w <= (NB - 1) + 2 * (kc - 1); ++w)
         for (int k = 0; k < kc; ++k) {
             const int b = w - 2 * k;
-            if (b >= 0 && b < NB) tab.push_back(((uint32_t)k << 16) | (uint32_t)b);
+            if (b >= h->b_lo && b < h->b_hi) tab.push_back(((uint32_t)k << 16) | (uint32_t)b);
         }
     uint32_t *d = nullptr;
     CU(cudaMalloc(&d, tab.size() * sizeof(uint32_t)));
@@ -272,13 +361,27 @@ static int lin_solve_exact(eq_fluid *h, const LinSolveReq *req, int nreq, int64_
             p.prob[i].a = req[i].a;
             p.prob[i].c_recip = 1.0f / req[i].c;                       // fluid.rs:311
             p.prob[i].orient = req[i].orient;
+            if (h->world > 1) {
+                const int fi = field_index(h, req[i].x);
+                if (fi < 0) return eq_fail(EQ_ERR_INVALID, "multi-GPU lin_solve needs one of the handle's fields");
+                if (h->rank > 0) {
+                    p.prob[i].x_up = h->peer_f[h->rank - 1][fi];
+                    p.prob[i].prog_up = h->peer_flags[h->rank - 1] + 8 + (size_t)i * prog_words;
+                }
+                if (h->rank + 1 < h->world) {
+                    p.prob[i].raw_down = h->peer_raw[h->rank + 1][i];
+                    p.prob[i].prog_down = h->peer_flags[h->rank + 1] + 8 + (size_t)i * prog_words;
+                }
+            }
         }
+        p.b_lo = h->b_lo;
+        p.b_hi = h->b_hi;
         p.codes = h->codes;
         p.chunk_flags = h->chunk_flags;
         p.row_fluid = h->row_fluid;
         p.col_fluid = h->col_fluid;
         p.jobs = jobs;
-        p.njobs = kc * NB;
+        p.njobs = kc * (h->b_hi - h->b_lo);
         p.N = L.N;
         p.P = L.P;
         p.K = kc;
@@ -304,9 +407,16 @@ static int lin_solve_exact(eq_fluid *h, const LinSolveReq *req, int nreq, int64_
         // ticket := 0, progress := 0; the sticky error word is left alone
         CU(cudaMemsetAsync(h->flags, 0, sizeof(unsigned), h->stream));
         CU(cudaMemsetAsync(h->flags + 8, 0, (size_t)nreq * prog_words * sizeof(unsigned), h->stream));
+        // Several GPUs: the exchange (a) gives my last band the neighbour's first row as its initial
+        // F_{-1} and (b) is a barrier with both neighbours, so nobody publishes into a progress
+        // mirror that has not been cleared yet.
+        for (int i = 0; i < nreq; ++i) TRY(halo_xchg(h, req[i].x));
         const int grid = std::min(h->lsx_ctas, p.njobs * nreq);
         EQ_LAUNCH(k_linsolve_exact, grid, LSX_THREADS, LSX_SMEM_BYTES, h->stream, p);
         TRY(check_launch("k_linsolve_exact"));
+        // ... and afterwards it waits until the neighbour's solver (which patches my last row and
+        // publishes into my mirrors until its very end) is done, then refreshes the ghost rows.
+        for (int i = 0; i < nreq; ++i) TRY(halo_xchg(h, req[i].x));
         done += kc;
     }
     for (int i = 0; i < nreq; ++i) {
@@ -319,13 +429,16 @@ static int lin_solve_exact(eq_fluid *h, const LinSolveReq *req, int nreq, int64_
 static int lin_solve_red_black(eq_fluid *h, const LinSolveReq *req, int nreq, int64_t iters) {
     const EqLayout L = h->L;
     const int threads = 256;
-    const dim3 grid((unsigned)((L.N / 2 + threads) / threads), (unsigned)(L.N - 2), 1);
+    const dim3 grid((unsigned)((L.N / 2 + threads) / threads), (unsigned)owned_interior_rows(h), 1);
     for (int64_t k = 0; k < iters; ++k) {
         for (int i = 0; i < nreq; ++i) {
             const float c_recip = 1.0f / req[i].c;
+            TRY(halo_xchg(h, req[i].x));            // each colour reads the other colour's ghost rows
             EQ_LAUNCH(k_rb_half, grid, threads, 0, h->stream, req[i].x, req[i].x0, req[i].a, c_recip, 0, L);
+            TRY(halo_xchg(h, req[i].x));
             EQ_LAUNCH(k_rb_half, grid, threads, 0, h->stream, req[i].x, req[i].x0, req[i].a, c_recip, 1, L);
             TRY(check_launch("k_rb_half"));
+            if (req[i].orient == EQ_ADJUST_COLUMN) TRY(halo_xchg(h, req[i].x));
             // fused into the same category: the boundary pass is part of the iteration
             if (req[i].orient == EQ_PASSIVE) {
                 EQ_LAUNCH(k_bnd_passive, (L.N + 255) / 256, 256, 0, h->stream, req[i].x, h->row_fluid, h->col_fluid, L);
@@ -337,13 +450,14 @@ static int lin_solve_red_black(eq_fluid *h, const LinSolveReq *req, int nreq, in
             TRY(check_launch("boundary in red-black"));
         }
     }
+    for (int i = 0; i < nreq; ++i) TRY(halo_xchg(h, req[i].x));
     return EQ_OK;
 }
 
 static int lin_solve(eq_fluid *h, const LinSolveReq *req, int nreq, int64_t iters) {
     if (iters <= 0) return EQ_OK;   // `for _k in 0..frames` runs zero times
     TRY(ensure_tables(h));
-    const int64_t cells = (int64_t)(h->L.N - 2) * (h->L.N - 2);
+    const int64_t cells = (int64_t)(h->L.N - 2) * owned_interior_rows(h);
     h->prof_cell_iters += cells * iters * nreq;
     if (h->prm.mode == EQ_MODE_RED_BLACK) {
         ProfScope ps(h, CAT_LS, (int)(3 * iters * nreq));
@@ -365,9 +479,10 @@ static LinSolveReq diffuse_req(const eq_fluid *h, int orient, float *x, const fl
 // project (fluid.rs:330-375)
 static int project(eq_fluid *h, float *vx, float *vy, float *p, float *div, int64_t iters) {
     const EqLayout L = h->L;
+    TRY(halo_xchg(h, vy));                                             // the stencil reads vy[j-1], vy[j+1]
     {
         ProfScope ps(h, CAT_PROJ, 1);
-        EQ_LAUNCH(k_divergence, row_grid(h, L.N - 2), 256, 0, h->stream, vx, vy, div, p, L);
+        EQ_LAUNCH(k_divergence, row_grid(h, owned_interior_rows(h)), 256, 0, h->stream, vx, vy, div, p, L);
         TRY(check_launch("k_divergence"));
     }
     TRY(set_boundaries(h, EQ_PASSIVE, div));                           // :351
@@ -376,7 +491,7 @@ static int project(eq_fluid *h, float *vx, float *vy, float *p, float *div, int6
     TRY(lin_solve(h, &r, 1, iters));                                   // :353-362
     {
         ProfScope ps(h, CAT_PROJ, 1);
-        EQ_LAUNCH(k_gradient, row_grid(h, L.N - 2), 256, 0, h->stream, vx, vy, p, L);
+        EQ_LAUNCH(k_gradient, row_grid(h, owned_interior_rows(h)), 256, 0, h->stream, vx, vy, p, L);
         TRY(check_launch("k_gradient"));
     }
     TRY(set_boundaries(h, EQ_ADJUST_ROW, vx));                         // :373
@@ -388,14 +503,17 @@ static int project(eq_fluid *h, float *vx, float *vy, float *p, float *div, int6
 static int advect(eq_fluid *h, int orientA, float *dA, const float *d0A, int orientB, float *dB,
                   const float *d0B, const float *vx, const float *vy) {
     const EqLayout L = h->L;
+    TRY(barrier_all(h));     // the back-trace may sample any rank's rows of d0: everybody must have produced them
     {
         ProfScope ps(h, CAT_ADV, 1);
+        const EqPeerTable tA = peer_table(h, d0A), tB = peer_table(h, d0B);
         if (dB)
-            EQ_LAUNCH((k_advect<2>), L.N - 2, 256, 0, h->stream, dA, d0A, dB, d0B, vx, vy, h->prm.delta_t, L);
+            EQ_LAUNCH((k_advect<2>), owned_interior_rows(h), 256, 16, h->stream, dA, tA, dB, tB, vx, vy, h->prm.delta_t, L);
         else
-            EQ_LAUNCH((k_advect<1>), L.N - 2, 256, 0, h->stream, dA, d0A, nullptr, nullptr, vx, vy, h->prm.delta_t, L);
+            EQ_LAUNCH((k_advect<1>), owned_interior_rows(h), 256, 16, h->stream, dA, tA, nullptr, tB, vx, vy, h->prm.delta_t, L);
         TRY(check_launch("k_advect"));
     }
+    TRY(barrier_all(h));     // ... and nobody may overwrite d0 while a neighbour still samples it
     TRY(set_boundaries(h, orientA, dA));                               // :431
     if (dB) TRY(set_boundaries(h, orientB, dB));
     return EQ_OK;
@@ -422,7 +540,9 @@ static int step_once(eq_fluid *h) {
     TRY(advect(h, EQ_PASSIVE, density, scratch, 0, nullptr, nullptr, vx, vy));     // :512-521
     {
         ProfScope ps(h, CAT_OTHER, 1);
-        CU(cudaMemcpyAsync(scratch, density, field_elems(h) * sizeof(float), cudaMemcpyDeviceToDevice,
+        const int r0 = std::max(0, h->L.row0 - 1), r1 = std::min(h->L.N, h->L.row1 + 1);   // slab + ghost rows
+        CU(cudaMemcpyAsync(scratch + (size_t)r0 * h->L.P, density + (size_t)r0 * h->L.P,
+                           (size_t)(r1 - r0) * h->L.P * sizeof(float), cudaMemcpyDeviceToDevice,
                            h->stream));                                // :523
     }
     h->prof_steps += 1;
@@ -439,7 +559,10 @@ static int validate_params(const EqParams *p) {
                        p->size);
     if (p->frames < 0 || p->gs_iterations < 0) return eq_fail(EQ_ERR_INVALID, "negative frames / gs_iterations");
     if (p->mode != EQ_MODE_EXACT && p->mode != EQ_MODE_RED_BLACK) return eq_fail(EQ_ERR_INVALID, "unknown mode %d", p->mode);
-    if (p->world > 1) return eq_fail(EQ_ERR_INVALID, "multi-GPU slabs are not implemented in this build");
+    if (p->world > EQ_MAX_RANKS) return eq_fail(EQ_ERR_INVALID, "world %d > %d", p->world, EQ_MAX_RANKS);
+    if (p->world > 1 && (p->rank < 0 || p->rank >= p->world)) return eq_fail(EQ_ERR_INVALID, "rank %d not in [0,%d)", p->rank, p->world);
+    if (p->world > 1 && ((int)p->size - 2 + 31) / 32 < p->world)
+        return eq_fail(EQ_ERR_INVALID, "grid too small for %d row slabs (one 32-row band per rank at least)", p->world);
     return EQ_OK;
 }
 
@@ -458,6 +581,17 @@ static int alloc_handle(const EqParams *params, eq_fluid **out) {
     h->L.N = (int)params->size;
     h->L.P = ((int)params->size + 31) / 32 * 32;
     h->L.rows = (int)params->size + EQ_ROW_PAD;
+    {
+        const int NBt = (h->L.N - 2 + 31) / 32;
+        h->world = std::max(1, (int)params->world);
+        h->rank = h->world > 1 ? params->rank : 0;
+        h->b_lo = (int)((int64_t)h->rank * NBt / h->world);
+        h->b_hi = (int)((int64_t)(h->rank + 1) * NBt / h->world);
+        h->L.row0 = h->rank == 0 ? 0 : 1 + 32 * h->b_lo;
+        h->L.row1 = h->rank == h->world - 1 ? h->L.N : 1 + 32 * h->b_hi;
+        h->L.rank = h->rank;
+        h->L.world = h->world;
+    }
     h->spans = new std::vector<ProfSpan>();
     h->ev_pool = new std::vector<cudaEvent_t>();
     h->job_tables = new std::map<int, uint32_t *>();
@@ -489,6 +623,13 @@ static int alloc_handle(const EqParams *params, eq_fluid **out) {
     h->flags_words = 8 + 2 * (size_t)LSX_KMAX * NB;
     CU(cudaMalloc(&h->flags, h->flags_words * sizeof(unsigned)));
     CU(cudaMemsetAsync(h->flags, 0, h->flags_words * sizeof(unsigned), h->stream));
+    CU(cudaMalloc(&h->sync, EQ_SYNC_WORDS * sizeof(unsigned)));
+    CU(cudaMemsetAsync(h->sync, 0, EQ_SYNC_WORDS * sizeof(unsigned), h->stream));
+    for (int i = 0; i < 6; ++i) h->peer_f[h->rank][i] = h->f[i];
+    h->peer_raw[h->rank][0] = h->raw[0];
+    h->peer_raw[h->rank][1] = h->raw[1];
+    h->peer_flags[h->rank] = h->flags;
+    h->peer_sync[h->rank] = h->sync;
     CU(cudaFuncSetAttribute(k_linsolve_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LSX_SMEM_BYTES));
     int per_sm = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_linsolve_exact, LSX_THREADS, LSX_SMEM_BYTES));
@@ -576,7 +717,16 @@ int eq_destroy(eq_fluid *h) {
     cudaFree(h->col_list);
     cudaFree(h->raw[0]);
     cudaFree(h->raw[1]);
+    for (int r = 0; r < EQ_MAX_RANKS; ++r)
+        if (h->peer_ipc[r]) {
+            for (int i = 0; i < 6; ++i) cudaIpcCloseMemHandle(h->peer_f[r][i]);
+            cudaIpcCloseMemHandle(h->peer_raw[r][0]);
+            cudaIpcCloseMemHandle(h->peer_raw[r][1]);
+            cudaIpcCloseMemHandle(h->peer_flags[r]);
+            cudaIpcCloseMemHandle(h->peer_sync[r]);
+        }
     cudaFree(h->flags);
+    cudaFree(h->sync);
     cudaFree(h->l2buf);
     if (h->job_tables) {
         for (auto &kv : *h->job_tables) cudaFree(kv.second);
@@ -615,6 +765,7 @@ int eq_create(const EqParams *params, eq_fluid **out) {
 int eq_clone(eq_fluid *h, eq_fluid **out) {
     NEED(h);
     if (!out) return eq_fail(EQ_ERR_INVALID, "null out pointer");
+    if (h->world > 1) return eq_fail(EQ_ERR_STATE, "eq_clone of a row-slab handle: download the owned rows instead");
     *out = nullptr;
     int r = alloc_handle(&h->prm, out);
     if (r != EQ_OK) {
@@ -839,6 +990,9 @@ int eq_download_rows(eq_fluid *h, int field, uint32_t row_begin, uint32_t n_rows
     TRY(field_ptr(h, field, &d, &es));
     const uint32_t N = (uint32_t)h->L.N;
     if (!host || row_begin > N || n_rows > N - row_begin) return eq_fail(EQ_ERR_INVALID, "bad row range");
+    if (h->world > 1 && n_rows > 0 && ((int)row_begin < h->L.row0 || (int)(row_begin + n_rows) > h->L.row1))
+        return eq_fail(EQ_ERR_INVALID, "rows [%u,%u) are not all owned by rank %d (owns [%d,%d))", row_begin,
+                       row_begin + n_rows, h->rank, h->L.row0, h->L.row1);
     if (n_rows > 0) {
         ProfScope ps(h, CAT_OTHER, 0);
         CU(cudaMemcpy2DAsync(host, (size_t)N * es, static_cast<char *>(d) + (size_t)row_begin * h->L.P * es,
@@ -856,6 +1010,7 @@ int eq_upload(eq_fluid *h, int field, const void *host, size_t bytes) {
 
 int eq_download(eq_fluid *h, int field, void *host, size_t bytes) {
     NEED(h);
+    if (h->world > 1) return eq_fail(EQ_ERR_STATE, "eq_download of a row-slab handle: use eq_owned_rows + eq_download_rows");
     const size_t es = field == EQ_F_CELLS ? 1 : sizeof(float);
     if (bytes != (size_t)h->L.N * h->L.N * es) return eq_fail(EQ_ERR_INVALID, "eq_download: expected %zu bytes, got %zu", (size_t)h->L.N * h->L.N * es, bytes);
     return eq_download_rows(h, field, 0, (uint32_t)h->L.N, host);
@@ -863,8 +1018,8 @@ int eq_download(eq_fluid *h, int field, void *host, size_t bytes) {
 
 int eq_owned_rows(eq_fluid *h, uint32_t *row_begin, uint32_t *row_end) {
     if (!h || !row_begin || !row_end) return eq_fail(EQ_ERR_INVALID, "null argument");
-    *row_begin = 0;
-    *row_end = (uint32_t)h->L.N;
+    *row_begin = (uint32_t)h->L.row0;
+    *row_end = (uint32_t)h->L.row1;
     return EQ_OK;
 }
 
@@ -936,7 +1091,8 @@ int eq_divergence_l2(eq_fluid *h, int vx_field, int vy_field, double *out) {
     double *d = nullptr;
     CU(cudaMalloc(&d, sizeof(double)));
     CU(cudaMemsetAsync(d, 0, sizeof(double), h->stream));
-    EQ_LAUNCH(k_divergence_sq, row_grid(h, h->L.N - 2), 256, 0, h->stream, vx, vy, d, h->L);
+    TRY(halo_xchg(h, vy));
+    EQ_LAUNCH(k_divergence_sq, row_grid(h, owned_interior_rows(h)), 256, 0, h->stream, vx, vy, d, h->L);
     int r = check_launch("k_divergence_sq");
     double v = 0.0;
     if (r == EQ_OK && cudaMemcpyAsync(&v, d, sizeof(double), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) r = EQ_ERR_CUDA;
@@ -1026,10 +1182,85 @@ int eq_l2_flush(eq_fluid *h) {
     return EQ_OK;
 }
 
-int eq_comm_unique_id(uint8_t id[128]) {
-    if (!id) return eq_fail(EQ_ERR_INVALID, "null id");
-    memset(id, 0, 128);
-    return eq_fail(EQ_ERR_COMM, "multi-GPU slabs are not implemented in this build");
+// ---- multi-GPU rendezvous ---------------------------------------------------------------
+// Each rank exports one blob; the launcher gathers them (torch.distributed / any side channel)
+// and hands every rank the concatenation.  Peers in other processes are mapped with CUDA IPC,
+// peers in the same process (several handles, one per device) with plain peer access.
+#define EQ_IPC_ITEMS 10
+struct EqIpcBlob {
+    uint32_t magic, rank, world, size;
+    int32_t device, pad;
+    int64_t pid;
+    uint64_t ptr[EQ_IPC_ITEMS];
+    cudaIpcMemHandle_t handle[EQ_IPC_ITEMS];
+};
+
+static void ipc_items(eq_fluid *h, void *items[EQ_IPC_ITEMS]) {
+    for (int i = 0; i < 6; ++i) items[i] = h->f[i];
+    items[6] = h->raw[0];
+    items[7] = h->raw[1];
+    items[8] = h->flags;
+    items[9] = h->sync;
+}
+
+int eq_ipc_blob_bytes(void) { return (int)sizeof(EqIpcBlob); }
+
+int eq_ipc_export(eq_fluid *h, void *blob, size_t capacity) {
+    NEED(h);
+    if (!blob || capacity < sizeof(EqIpcBlob)) return eq_fail(EQ_ERR_INVALID, "blob buffer too small (%zu needed)", sizeof(EqIpcBlob));
+    CU(cudaStreamSynchronize(h->stream));   // allocations are zeroed before anybody maps them
+    EqIpcBlob b;
+    memset(&b, 0, sizeof(b));
+    b.magic = 0x45514950u;
+    b.rank = (uint32_t)h->rank;
+    b.world = (uint32_t)h->world;
+    b.size = h->prm.size;
+    b.device = h->dev;
+    b.pid = (int64_t)getpid();
+    void *items[EQ_IPC_ITEMS];
+    ipc_items(h, items);
+    for (int i = 0; i < EQ_IPC_ITEMS; ++i) {
+        b.ptr[i] = (uint64_t)(uintptr_t)items[i];
+        CU(cudaIpcGetMemHandle(&b.handle[i], items[i]));
+    }
+    memcpy(blob, &b, sizeof(b));
+    return EQ_OK;
+}
+
+int eq_ipc_attach(eq_fluid *h, const void *blobs, size_t blob_bytes, int world) {
+    NEED(h);
+    if (!blobs || blob_bytes != sizeof(EqIpcBlob) || world != h->world)
+        return eq_fail(EQ_ERR_INVALID, "eq_ipc_attach: need %d blobs of %zu bytes", h->world, sizeof(EqIpcBlob));
+    for (int r = 0; r < world; ++r) {
+        EqIpcBlob b;
+        memcpy(&b, static_cast<const char *>(blobs) + (size_t)r * blob_bytes, sizeof(b));
+        if (b.magic != 0x45514950u || (int)b.rank != r || (int)b.world != world || b.size != h->prm.size)
+            return eq_fail(EQ_ERR_COMM, "blob %d does not describe rank %d of %d for a %u grid", r, r, world, h->prm.size);
+        if (r == h->rank) continue;
+        void *mapped[EQ_IPC_ITEMS];
+        if (b.pid == (int64_t)getpid()) {
+            if (b.device != h->dev) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                    return eq_fail(EQ_ERR_COMM, "cudaDeviceEnablePeerAccess(%d) failed: %s", b.device, cudaGetErrorString(e));
+                cudaGetLastError();
+            }
+            for (int i = 0; i < EQ_IPC_ITEMS; ++i) mapped[i] = (void *)(uintptr_t)b.ptr[i];
+        } else {
+            for (int i = 0; i < EQ_IPC_ITEMS; ++i) {
+                cudaError_t e = cudaIpcOpenMemHandle(&mapped[i], b.handle[i], cudaIpcMemLazyEnablePeerAccess);
+                if (e != cudaSuccess) return eq_fail(EQ_ERR_COMM, "cudaIpcOpenMemHandle (rank %d, item %d) failed: %s", r, i, cudaGetErrorString(e));
+            }
+            h->peer_ipc[r] = true;
+        }
+        for (int i = 0; i < 6; ++i) h->peer_f[r][i] = static_cast<float *>(mapped[i]);
+        h->peer_raw[r][0] = static_cast<float *>(mapped[6]);
+        h->peer_raw[r][1] = static_cast<float *>(mapped[7]);
+        h->peer_flags[r] = static_cast<unsigned *>(mapped[8]);
+        h->peer_sync[r] = static_cast<unsigned *>(mapped[9]);
+    }
+    h->attached = true;
+    return EQ_OK;
 }
 
 }  // extern "C"

@@ -39,9 +39,42 @@ struct EqLayout {
     int N;      // grid is N x N
     int P;      // row pitch in elements
     int rows;   // allocated rows = N + EQ_ROW_PAD
+    // Row slab owned by this rank (multi-GPU).  Every rank allocates the full grid and
+    // uses global coordinates; only rows [row0, row1) are authoritative here, rows row0-1 and row1
+    // are ghost copies refreshed by k_halo_exchange.  Single GPU: row0 = 0, row1 = N.
+    int row0, row1;
+    int rank, world;
 };
 
+#define EQ_MAX_RANKS 8
+// where each rank keeps a field, and which rows it owns (for gathers that leave the slab)
+struct EqPeerTable {
+    const float *base[EQ_MAX_RANKS];
+    int row_begin[EQ_MAX_RANKS + 1];
+    int world;
+};
+__device__ __forceinline__ const float *eq_owner_base(const EqPeerTable &t, unsigned j) {
+    int r = 0;
+#pragma unroll
+    for (int i = 1; i < EQ_MAX_RANKS; ++i)
+        if (i < t.world && (int)j >= t.row_begin[i]) r = i;
+    return t.base[r];
+}
+
 #ifndef EQ_HOST_EMU
+__device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned ld_relaxed_sys_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u32(unsigned *p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
     unsigned v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");

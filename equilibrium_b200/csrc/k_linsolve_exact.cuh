@@ -77,6 +77,10 @@ struct LsxProblem {
     unsigned *progress;  // [K][NB] chunks completed
     float a, c_recip;
     int orient;          // EqOrientation
+    // row slabs over several GPUs: the same arrays on rank-1 / rank+1 (nullptr on one GPU)
+    float *x_up;         // rank-1's x: my first band writes its first row and its DOWN patches there
+    float *raw_down;     // rank+1's raw stream: my last band writes R_k of its last row there
+    unsigned *prog_up, *prog_down;   // the neighbours' mirrors of my boundary bands' progress
 };
 
 struct LsxParams {
@@ -89,6 +93,7 @@ struct LsxParams {
     const uint32_t *jobs;        // [K*NB] (k << 16 | b) in wavefront order
     int njobs;                   // K*NB (per problem)
     int N, P, K, NB, NC;
+    int b_lo, b_hi;              // bands [b_lo, b_hi) are mine (row slab)
     unsigned *ticket;
     int *error;
     int slack;                   // a consumer asks its producers to be this many chunks further ahead than strictly needed
@@ -113,15 +118,17 @@ __device__ __forceinline__ unsigned long long lsx_gtime() { unsigned long long t
 
 // ---- waiting primitives: lane 0 waits, the result is broadcast; every loop can be aborted ----
 // Dependency flags of other jobs (global memory, acquire).
-__device__ __forceinline__ bool lsx_wait_flags(const unsigned *f1, unsigned n1, const unsigned *f2, unsigned n2,
-                                               int *error, int lane) {
+__device__ __forceinline__ bool lsx_wait_flags(const unsigned *f1, unsigned n1, bool sys1, const unsigned *f2, unsigned n2,
+                                               bool sys2, int *error, int lane) {
     int ok = 1;
     if (lane == 0) {
         unsigned spins = 0;
         // spin with relaxed loads (an acquire load is followed by an L1 invalidate, CCTL.IVALL, which
         // the five loaders of an SM would otherwise issue every few hundred cycles), then take one
         // acquire load of the flag that was seen set: it reads from the release and synchronises.
-        while ((f1 && ld_relaxed_u32(f1) < n1) || (f2 && ld_relaxed_u32(f2) < n2)) {
+        // (a flag written by the neighbouring GPU is read at system scope)
+        while ((f1 && (sys1 ? ld_relaxed_sys_u32(f1) : ld_relaxed_u32(f1)) < n1) ||
+               (f2 && (sys2 ? ld_relaxed_sys_u32(f2) : ld_relaxed_u32(f2)) < n2)) {
             __nanosleep(64);
             if ((++spins & 1023u) == 0) {
                 if (spins >= LSX_SPIN_LIMIT) {
@@ -136,8 +143,8 @@ __device__ __forceinline__ bool lsx_wait_flags(const unsigned *f1, unsigned n1, 
             }
         }
         if (ok) {
-            if (f1) (void)ld_acquire_u32(f1);
-            if (f2) (void)ld_acquire_u32(f2);
+            if (f1) (void)(sys1 ? ld_acquire_sys_u32(f1) : ld_acquire_u32(f1));
+            if (f2) (void)(sys2 ? ld_acquire_sys_u32(f2) : ld_acquire_u32(f2));
         }
     }
     ok = __shfl_sync(0xffffffffu, ok, 0);
@@ -177,6 +184,7 @@ struct LsxJob {
     int b, k, lane;
     int N, P, NC, NB, j0, M;
     bool last_band;
+    bool first_local, last_local;   // my slab's first / last band has its neighbour on another GPU
     const uint8_t *cflags;
 
     __device__ __forceinline__ LsxJob(const LsxParams &p_, const LsxProblem &pr_, uint32_t sbase_, int b_, int k_,
@@ -186,6 +194,8 @@ struct LsxJob {
         j0 = 1 + 32 * b;
         M = (N + 31 + LSX_CW - 1) / LSX_CW;           // steps 0 .. N+30 in macro steps of LSX_CW
         last_band = (b == NB - 1);
+        first_local = (b == p.b_lo && b > 0);
+        last_local = (b == p.b_hi - 1 && b < NB - 1);
         cflags = p.chunk_flags + (ORIENT == EQ_ADJUST_COLUMN ? (size_t)NB * NC : 0) + (size_t)b * NC;
     }
     __device__ __forceinline__ uint32_t bar_full(int q) const { return sbase + LSX_BAR_OFF + (uint32_t)(q % LSX_SLOTS) * 16u; }
@@ -240,8 +250,8 @@ struct LsxJob {
             LSX_TRACE(0, q);
             // ... and the producers of this chunk must have published it
             if (!p.debug_nodeps &&
-                !lsx_wait_flags(flag_prev_iter, (unsigned)min(q + 1 + p.slack, NC), flag_band_above,
-                                (unsigned)min(q + 1 + p.slack, NC), p.error, lane))
+                !lsx_wait_flags(flag_prev_iter, (unsigned)min(q + 1 + p.slack, NC), last_local, flag_band_above,
+                                (unsigned)min(q + 1 + p.slack, NC), first_local, p.error, lane))
                 return false;
             if (p.stats) { const long long t2 = lsx_clock(); LSX_STAT(7, t1 - t0); LSX_STAT(8, t2 - t1); }
             const uint32_t slot = (uint32_t)(q % LSX_SLOTS) * (LSX_CW * 4u);   // byte offset of the chunk in a 512 B row
@@ -293,7 +303,7 @@ struct LsxJob {
     // PUBLISHER's job, so the ring keeps moving while a release is in flight.
     __device__ __forceinline__ bool run_storer() const {
         float *__restrict__ x = pr.x;
-        float *raw_out = (b + 1 < NB) ? pr.raw + (size_t)(b + 1) * P : nullptr;
+        float *raw_out = (b + 1 < NB) ? (last_local ? pr.raw_down : pr.raw) + (size_t)(b + 1) * P : nullptr;
         const uint32_t raw_s = sbase + LSX_RAW_OFF;
         constexpr int LPR = LSX_CW / 4, RPP = 32 / LPR;
         const int sub = lane % LPR, rr = lane / LPR;
@@ -331,6 +341,11 @@ struct LsxJob {
                 }
             }
             if (raw_out && lane < LSX_CW) raw_out[col0 + lane] = lds_f32(raw_s + (uint32_t)((col0 + lane) & 127) * 4u);
+            if (first_local && lane < LPR) {
+                // my first row is row j0+32 of the last band on rank-1: keep its copy there current
+                const float4 v = lds_f32x4(sbase + LSX_XS_OFF + 512u + slot + 16u * lane);
+                *reinterpret_cast<float4 *>(pr.x_up + (size_t)j0 * P + col0 + 4 * lane) = v;
+            }
             __syncwarp();                             // every lane's smem reads and global stores are issued
             if (lane == 0) {
                 mbar_arrive(bar_free(q));             // the ring slot may be refilled
@@ -367,6 +382,8 @@ struct LsxJob {
                     const long long t2 = p.stats ? lsx_clock() : 0;
                     LSX_TRACE(6, q - 1);
                     st_release_u32(my_flag, (unsigned)q);
+                    if (first_local) st_release_sys_u32(pr.prog_up + (size_t)k * NB + b, (unsigned)q);
+                    if (last_local) st_release_sys_u32(pr.prog_down + (size_t)k * NB + b, (unsigned)q);
                     LSX_TRACE(7, q - 1);
                     if (p.stats) { const long long t3 = lsx_clock(); LSX_STAT(12, t3 - t2); LSX_STAT(9, 1); }
                 }
@@ -383,7 +400,7 @@ struct LsxJob {
         const int tr = lane + 1;
         const bool in_row = (j <= N - 2);
         const float a = pr.a, c_recip = pr.c_recip;
-        float *__restrict__ x = pr.x;
+        float *__restrict__ x = first_local ? pr.x_up : pr.x;   // only used for the cross-band DOWN patch of row j0-1
         const bool row_has_fluid = (ORIENT == EQ_PASSIVE && in_row) ? (p.row_fluid[j] != 0) : false;
         // shared addresses of this lane's rows
         const uint32_t xs_row = sbase + LSX_XS_OFF + (uint32_t)tr * 512u;     // own row

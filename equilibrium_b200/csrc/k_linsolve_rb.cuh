@@ -9,7 +9,7 @@
 // v1: one launch per colour.  Thread t of row j owns cell i = 1 + 2t + off.
 __global__ void __launch_bounds__(256) k_rb_half(float *__restrict__ x, const float *__restrict__ x0, float a,
                                                  float c_recip, int colour, EqLayout L) {
-    const int j = blockIdx.y + 1;
+    const int j = blockIdx.y + max(L.row0, 1);   // owned interior rows
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = 1 + 2 * t + ((colour ^ (j + 1)) & 1);
     if (i > L.N - 2) return;

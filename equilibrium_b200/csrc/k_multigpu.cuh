@@ -1,0 +1,87 @@
+// k_multigpu.cuh -- row-slab decomposition across GPUs: halo rows and barriers.
+//
+// One process per GPU; every rank maps its neighbours' arrays (CUDA IPC, or plain peer access
+// inside one process) and kernels read / write peer memory directly over NVLink: there is no
+// host round trip and no library collective on the data path.  Cross-GPU ordering uses
+// system-scope release/acquire on small flag arrays that live in the *consumer's* memory (the
+// producer stores remotely, the consumer polls locally).
+#pragma once
+#include "eq_common.cuh"
+
+#define EQ_SYNC_WORDS 32          // [0..3] halo slots (up A/B, down A/B), [8..15] all-rank barrier
+#define EQ_XGPU_SPIN_LIMIT (1u << 24)
+
+struct EqHaloArgs {
+    float *field;                 // my copy
+    float *peer_up, *peer_down;   // the same field on rank-1 / rank+1 (nullptr at the ends)
+    unsigned *sync;               // my slots, written by the neighbours
+    unsigned *sync_up, *sync_down;// the neighbours' slots
+    unsigned epoch;
+    int *error;
+};
+
+__device__ __forceinline__ bool eq_xgpu_wait(const unsigned *slot, unsigned epoch, int *error) {
+    unsigned spins = 0;
+    while (ld_relaxed_sys_u32(slot) < epoch) {
+        __nanosleep(100);
+        if ((++spins & 4095u) == 0) {
+            if (spins >= EQ_XGPU_SPIN_LIMIT) {
+                *error = 4;
+                return false;
+            }
+            if (ld_volatile_s32(error) != 0) return false;
+        }
+    }
+    (void)ld_acquire_sys_u32(slot);
+    return true;
+}
+
+// Block 0 talks to rank-1, block 1 to rank+1.  Phase A: "everything I launched before this kernel
+// (including my writes into your memory) is done" -- exchanged before any row is copied, because
+// the neighbour's solver may still be patching my boundary row.  Phase B: push my boundary row
+// into the neighbour's ghost row, then "pushed".
+__global__ void __launch_bounds__(1024) k_halo_exchange(EqHaloArgs a, EqLayout L) {
+    const int dir = blockIdx.x;
+    float *peer = dir == 0 ? a.peer_up : a.peer_down;
+    if (!peer) return;
+    unsigned *peer_sync = dir == 0 ? a.sync_up : a.sync_down;
+    const unsigned *mine = a.sync + dir * 2;
+    unsigned *theirs = peer_sync + (1 - dir) * 2;          // I am the neighbour's (1-dir) side
+    EQ_DYN_SMEM(halo_smem);
+    int &ok = *reinterpret_cast<int *>(halo_smem);
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        st_release_sys_u32(theirs + 0, a.epoch);
+        ok = eq_xgpu_wait(mine + 0, a.epoch, a.error) ? 1 : 0;
+    }
+    __syncthreads();
+    if (!ok) return;
+    const int row = dir == 0 ? L.row0 : L.row1 - 1;       // first / last owned row
+    const float4 *src = reinterpret_cast<const float4 *>(a.field + (size_t)row * L.P);
+    float4 *dst = reinterpret_cast<float4 *>(peer + (size_t)row * L.P);
+    for (int i = threadIdx.x; i < L.P / 4; i += blockDim.x) dst[i] = src[i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        st_release_sys_u32(theirs + 1, a.epoch);
+        eq_xgpu_wait(mine + 1, a.epoch, a.error);
+    }
+}
+
+struct EqBarrierArgs {
+    unsigned *sync;                       // my slots
+    unsigned *peer_sync[EQ_MAX_RANKS];    // everybody's slots
+    int rank, world;
+    unsigned epoch;
+    int *error;
+};
+
+// All ranks: "everything I launched before this kernel is done" (needed around advect, whose
+// back-trace may read any rank's rows).
+__global__ void k_barrier_all(EqBarrierArgs a) {
+    const int i = threadIdx.x;
+    if (i >= a.world || i == a.rank) return;
+    __threadfence_system();
+    st_release_sys_u32(a.peer_sync[i] + 8 + a.rank, a.epoch);
+    eq_xgpu_wait(a.sync + 8 + i, a.epoch, a.error);
+}

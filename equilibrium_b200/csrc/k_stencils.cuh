@@ -42,17 +42,18 @@ __global__ void k_build_codes(const uint8_t *__restrict__ cells, uint8_t *__rest
         }
         // (band, chunk) summaries for the wavefront solver: band = 32 rows from row 1, chunk = EQ_LSX_CW columns
         const int NB = (L.N - 2 + 31) / 32, NC = (L.N + EQ_LSX_CW - 1) / EQ_LSX_CW;
+        const bool owned = (j >= L.row0 && j < L.row1);   // the sparse lists drive stand-alone boundary passes
         if (code & 3u) {
-            atomicAdd(&counts[0], 1u);
+            if (owned) atomicAdd(&counts[0], 1u);
             chunk_flags[(size_t)((j - 1) / 32) * NC + i / EQ_LSX_CW] = 1;
         }
         if (code & 12u) {
-            atomicAdd(&counts[1], 1u);
+            if (owned) atomicAdd(&counts[1], 1u);
             chunk_flags[(size_t)NB * NC + (size_t)((j - 1) / 32) * NC + i / EQ_LSX_CW] = 1;
             if (j / 32 < NB)   // row j is also row j0-1 of the band below (cross-band DOWN patch)
                 chunk_flags[(size_t)NB * NC + (size_t)(j / 32) * NC + i / EQ_LSX_CW] = 1;
         }
-    } else {
+    } else if (j >= L.row0 && j < L.row1) {
         if (code & 3u) {
             const unsigned slot = atomicAdd(&counts[2], 1u);
             row_list[slot] = make_uint2(o, (code & 3u) == EQ_CODE_ROW_RIGHT ? o + 1u : o - 1u);
@@ -65,17 +66,23 @@ __global__ void k_build_codes(const uint8_t *__restrict__ cells, uint8_t *__rest
 }
 
 // 4 corners (fluid.rs:265-271) from the *current* frame values.
-__device__ __forceinline__ void eq_corners(float *x, int N, int P) {
+// (the top corners belong to the rank that owns row 0, the bottom ones to the owner of row N-1)
+__device__ __forceinline__ void eq_corners(float *x, const EqLayout &L) {
+    const int N = L.N, P = L.P;
     const size_t last = (size_t)(N - 1) * P;
     const size_t prev = (size_t)(N - 2) * P;
-    x[0] = __fmul_rn(0.5f, __fadd_rn(x[1], x[P]));
-    x[last] = __fmul_rn(0.5f, __fadd_rn(x[last + 1], x[prev]));
-    x[N - 1] = __fmul_rn(0.5f, __fadd_rn(x[N - 2], x[(size_t)P + N - 1]));
-    x[last + N - 1] = __fmul_rn(0.5f, __fadd_rn(x[last + N - 2], x[prev + N - 1]));
+    if (L.row0 == 0) {
+        x[0] = __fmul_rn(0.5f, __fadd_rn(x[1], x[P]));
+        x[N - 1] = __fmul_rn(0.5f, __fadd_rn(x[N - 2], x[(size_t)P + N - 1]));
+    }
+    if (L.row1 == N) {
+        x[last] = __fmul_rn(0.5f, __fadd_rn(x[last + 1], x[prev]));
+        x[last + N - 1] = __fmul_rn(0.5f, __fadd_rn(x[last + N - 2], x[prev + N - 1]));
+    }
 }
 
 __global__ void k_corners(float *x, EqLayout L) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) eq_corners(x, L.N, L.P);
+    if (blockIdx.x == 0 && threadIdx.x == 0) eq_corners(x, L);
 }
 
 // set_boundaries(AdjustRow | AdjustColumn): x[dst] = -x[src] for the listed
@@ -87,7 +94,7 @@ __global__ void k_bnd_list(float *x, const uint2 *__restrict__ list, unsigned n,
         const uint2 e = list[t];
         x[e.x] = -x[e.y];
     }
-    if (t == 0) eq_corners(x, L.N, L.P);
+    if (t == 0) eq_corners(x, L);
 }
 
 // set_boundaries(Passive) (fluid.rs:179-187 + quirk Q6) and the corners.  The
@@ -99,10 +106,10 @@ __global__ void k_bnd_passive(float *x, const uint8_t *__restrict__ row_fluid,
     const int t = blockIdx.x * blockDim.x + threadIdx.x;   // 1 .. N-2
     if (t >= 1 && t <= N - 2) {
         if (col_fluid[t]) {
-            x[t] = x[t + (size_t)P];
-            x[t + (size_t)(N - 1) * P] = x[t + (size_t)(N - 2) * P];
+            if (L.row0 == 0) x[t] = x[t + (size_t)P];
+            if (L.row1 == N) x[t + (size_t)(N - 1) * P] = x[t + (size_t)(N - 2) * P];
         }
-        if (row_fluid[t]) {
+        if (row_fluid[t] && t >= L.row0 && t < L.row1) {
             x[(size_t)t * P] = x[(size_t)t * P + 1];
             x[(size_t)t * P + N - 1] = x[(size_t)t * P + N - 2];
         }
@@ -118,10 +125,14 @@ __global__ void k_bnd_passive(float *x, const uint8_t *__restrict__ row_fluid,
         const float bl0 = w1 ? x[r1 + N - 2] : x[r1 + N - 1];    // x[N-1,1]
         const float all_ = cl ? x[rp + N - 2] : x[rl + N - 2];   // x[N-2,N-1]
         const float bll = wl ? x[rp + N - 2] : x[rp + N - 1];    // x[N-1,N-2]
-        x[0] = __fmul_rn(0.5f, __fadd_rn(a00, b00));
-        x[rl] = __fmul_rn(0.5f, __fadd_rn(a0l, b0l));
-        x[N - 1] = __fmul_rn(0.5f, __fadd_rn(al0, bl0));
-        x[rl + N - 1] = __fmul_rn(0.5f, __fadd_rn(all_, bll));
+        if (L.row0 == 0) {
+            x[0] = __fmul_rn(0.5f, __fadd_rn(a00, b00));
+            x[N - 1] = __fmul_rn(0.5f, __fadd_rn(al0, bl0));
+        }
+        if (L.row1 == N) {
+            x[rl] = __fmul_rn(0.5f, __fadd_rn(a0l, b0l));
+            x[rl + N - 1] = __fmul_rn(0.5f, __fadd_rn(all_, bll));
+        }
     }
 }
 
@@ -131,7 +142,7 @@ __global__ void k_bnd_passive(float *x, const uint8_t *__restrict__ row_fluid,
 __global__ void k_divergence(const float *__restrict__ vx, const float *__restrict__ vy,
                              float *__restrict__ div, float *__restrict__ p, EqLayout L) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int j = blockIdx.y + 1;
+    const int j = blockIdx.y + max(L.row0, 1);              // owned interior rows
     if (i < 1 || i > L.N - 2) return;
     const size_t o = (size_t)i + (size_t)j * L.P;
     float t = __fsub_rn(vx[o + 1], vx[o - 1]);
@@ -145,7 +156,7 @@ __global__ void k_divergence(const float *__restrict__ vx, const float *__restri
 __global__ void k_gradient(float *__restrict__ vx, float *__restrict__ vy,
                            const float *__restrict__ p, EqLayout L) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int j = blockIdx.y + 1;
+    const int j = blockIdx.y + max(L.row0, 1);
     if (i < 1 || i > L.N - 2) return;
     const size_t o = (size_t)i + (size_t)j * L.P;
     const float nf = (float)L.N;
@@ -195,25 +206,29 @@ __device__ __forceinline__ AdvSample eq_backtrace(int i, int j, float u, float v
     return r;
 }
 
-__device__ __forceinline__ float eq_bilinear(const AdvSample &r, const float *__restrict__ d0, int P) {
-    const float a = d0[r.i0 + (size_t)r.j0 * P], b = d0[r.i0 + (size_t)r.j1 * P];
-    const float c = d0[r.i1 + (size_t)r.j0 * P], d = d0[r.i1 + (size_t)r.j1 * P];
+// The back-trace may leave the slab: each sample row is read from the rank that owns it (direct
+// peer loads over NVLink; one rank => the local array).
+__device__ __forceinline__ float eq_bilinear(const AdvSample &r, const EqPeerTable &t, int P) {
+    const float *lo = eq_owner_base(t, r.j0), *hi = eq_owner_base(t, r.j1);
+    const float a = lo[r.i0 + (size_t)r.j0 * P], b = hi[r.i0 + (size_t)r.j1 * P];
+    const float c = lo[r.i1 + (size_t)r.j0 * P], d = hi[r.i1 + (size_t)r.j1 * P];
     const float l = __fadd_rn(__fmul_rn(r.t0, a), __fmul_rn(r.t1, b));
     const float h = __fadd_rn(__fmul_rn(r.t0, c), __fmul_rn(r.t1, d));
     return __fadd_rn(__fmul_rn(r.s0, l), __fmul_rn(r.s1, h));          // :424-428
 }
 
 template <int NF>
-__global__ void __launch_bounds__(256) k_advect(float *__restrict__ dA, const float *__restrict__ d0A,
-                                                float *__restrict__ dB, const float *__restrict__ d0B,
+__global__ void __launch_bounds__(256) k_advect(float *__restrict__ dA, const EqPeerTable d0A,
+                                                float *__restrict__ dB, const EqPeerTable d0B,
                                                 const float *__restrict__ vx, const float *__restrict__ vy,
                                                 float dt, EqLayout L) {
     const int N = L.N, P = L.P;
-    const int j = blockIdx.x + 1;
+    const int j = blockIdx.x + max(L.row0, 1);              // owned interior rows
     const float nf = (float)N;
     const float dtx = __fmul_rn(dt, (float)(N - 2));                   // :390
     const size_t row = (size_t)j * P;
-    __shared__ int s_first;
+    EQ_DYN_SMEM(adv_smem);
+    int &s_first = *reinterpret_cast<int *>(adv_smem);
     if (threadIdx.x == 0) s_first = N;
     __syncthreads();
     int mine = N;
@@ -285,7 +300,7 @@ __global__ void k_set_cells_rect(uint8_t *cells, int x0, int y0, int x1, int y1,
 __global__ void k_divergence_sq(const float *__restrict__ vx, const float *__restrict__ vy, double *out,
                                 EqLayout L) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int j = blockIdx.y + 1;
+    const int j = blockIdx.y + max(L.row0, 1);
     double v = 0.0;
     if (i >= 1 && i <= L.N - 2) {
         const size_t o = (size_t)i + (size_t)j * L.P;

@@ -36,7 +36,8 @@ class Fluid:
     def __init__(self, fluid_configs: FluidConfigs | None = None,
                  simulation_configs: SimulationConfigs | None = None, *,
                  mode: str = "exact", gs_iterations: int = 0, device: int = 0,
-                 noise_seed: int = 0, lib_path: str | None = None, _handle=None):
+                 noise_seed: int = 0, lib_path: str | None = None, rank: int = 0, world: int = 1,
+                 _handle=None):
         """Fluid::new (fluid.rs:93-110).  Extra keyword-only knobs the CUDA path adds:
         mode ('exact' | 'red_black'), gs_iterations (0 => `frames`, quirk Q1), device."""
         self._lib = _lib.load(lib_path)
@@ -45,6 +46,7 @@ class Fluid:
         self._mode = {"exact": _lib.MODE_EXACT, "red_black": _lib.MODE_RED_BLACK}[mode]
         self._gs_iterations = int(gs_iterations)
         self._device = int(device)
+        self._rank, self._world = int(rank), int(world)
         self._rng = np.random.default_rng(noise_seed)
         self._pushed = None
         if _handle is not None:
@@ -78,7 +80,7 @@ class Fluid:
         p.viscosity = float(self.fluid_configs.viscousity)
         p.mode = self._mode
         p.device = self._device
-        p.rank, p.world = 0, 1
+        p.rank, p.world = self._rank, self._world
         return p
 
     def _params_tuple(self):
@@ -176,6 +178,44 @@ class Fluid:
     def sync(self):
         _lib.check(self._lib, self._lib.eq_sync(self._h))
 
+    # -- row slabs over several GPUs --------------------------------
+    @property
+    def rank(self) -> int:
+        return self._rank
+
+    @property
+    def world(self) -> int:
+        return self._world
+
+    def ipc_blob(self) -> bytes:
+        """This rank's rendezvous blob (eq_ipc_export)."""
+        n = self._lib.eq_ipc_blob_bytes()
+        buf = C.create_string_buffer(n)
+        _lib.check(self._lib, self._lib.eq_ipc_export(self._h, buf, n))
+        return buf.raw
+
+    def ipc_attach(self, blobs):
+        """Map every rank's arrays (eq_ipc_attach); `blobs` in rank order."""
+        n = self._lib.eq_ipc_blob_bytes()
+        assert len(blobs) == self._world and all(len(b) == n for b in blobs)
+        joined = b"".join(blobs)
+        _lib.check(self._lib, self._lib.eq_ipc_attach(self._h, joined, n, self._world))
+
+    def owned_rows(self):
+        a, b = C.c_uint32(), C.c_uint32()
+        _lib.check(self._lib, self._lib.eq_owned_rows(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def download_owned(self, name: str):
+        """(row_begin, rows) of the slab this rank owns."""
+        fid = self.FIELDS[name]
+        n = int(self.simulation_configs.size)
+        r0, r1 = self.owned_rows()
+        dt = np.uint8 if fid == _lib.F_CELLS else np.float32
+        out = np.empty((r1 - r0, n), dtype=dt)
+        _lib.check(self._lib, self._lib.eq_download_rows(self._h, fid, r0, r1 - r0, out.ctypes.data))
+        return r0, out
+
     # -- field access -----------------------------------------------------------
     def download(self, name: str, out: np.ndarray | None = None) -> np.ndarray:
         fid = self.FIELDS[name]
@@ -247,3 +287,19 @@ class Fluid:
 
     def set_stream(self, cuda_stream_ptr: int | None):
         _lib.check(self._lib, self._lib.eq_set_stream(self._h, cuda_stream_ptr))
+
+
+def connect_local(fluids):
+    """Several row-slab handles living in ONE process (one per device): exchange blobs directly."""
+    blobs = [f.ipc_blob() for f in fluids]
+    for f in fluids:
+        f.ipc_attach(blobs)
+
+
+def connect_distributed(fluid: Fluid, group=None):
+    """One process per GPU: gather the blobs with torch.distributed (plumbing only) and attach."""
+    import torch.distributed as dist
+    blobs = [None] * dist.get_world_size(group)
+    dist.all_gather_object(blobs, fluid.ipc_blob(), group=group)
+    fluid.ipc_attach(blobs)
+    dist.barrier(group)

@@ -81,7 +81,7 @@ typedef struct EqParams {
      * (SURVEY.md 8e).  world <= 1: single GPU, the other fields are ignored. */
     int32_t rank;
     int32_t world;
-    uint8_t comm_id[128];   /* opaque id from eq_comm_unique_id(), same on all ranks */
+    uint8_t comm_id[128];   /* reserved */
 } EqParams;
 
 /* Point source applied before the step of frame `frame` (what add_noise does,
@@ -186,9 +186,13 @@ int eq_host_alloc(void **out, size_t bytes);         /* cudaHostAlloc (pinned) *
 int eq_host_free(void *p);
 int eq_l2_flush(eq_fluid *h);                        /* overwrite a buffer larger than L2 */
 
-/* Multi-GPU rendezvous: rank 0 creates the id, the launcher broadcasts it
- * (torch.distributed / any side channel) and every rank passes it in EqParams. */
-int eq_comm_unique_id(uint8_t id[128]);
+/* Multi-GPU rendezvous (row slabs, one process per GPU): after eq_create with world > 1 every
+ * rank exports a blob of eq_ipc_blob_bytes() bytes, the launcher gathers them
+ * (torch.distributed / any side channel) and every rank attaches the rank-ordered
+ * concatenation.  Neighbours are then read and written directly over NVLink by the kernels. */
+int eq_ipc_blob_bytes(void);
+int eq_ipc_export(eq_fluid *h, void *blob, size_t capacity);
+int eq_ipc_attach(eq_fluid *h, const void *blobs, size_t blob_bytes, int world);
 
 #ifdef __cplusplus
 }

@@ -117,10 +117,14 @@ static inline T __shfl_sync(unsigned, T v, int src) {
 }
 
 // ---- memory model stand-ins --------------------------------------------------
+static inline void __threadfence_system() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 static inline void __nanosleep(unsigned) { std::this_thread::yield(); }
 static inline unsigned ld_acquire_u32(const unsigned *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
 static inline void st_release_u32(unsigned *p, unsigned v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+static inline unsigned ld_acquire_sys_u32(const unsigned *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+static inline unsigned ld_relaxed_sys_u32(const unsigned *p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
+static inline void st_release_sys_u32(unsigned *p, unsigned v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 static inline int ld_volatile_s32(const int *p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
 static inline void cp_async_16(void *smem, const void *gmem) { memcpy(smem, gmem, 16); }
 static inline unsigned ld_relaxed_u32(const unsigned *p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
@@ -237,6 +241,12 @@ static inline cudaError_t cudaMemcpy2DAsync(void *d, size_t dp, const void *s, s
 }
 static inline cudaError_t cudaHostAlloc(void **p, size_t n, unsigned) { *p = malloc(n); return *p ? cudaSuccess : 2; }
 static inline cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
+struct cudaIpcMemHandle_t { char reserved[64]; };
+enum { cudaIpcMemLazyEnablePeerAccess = 1, cudaErrorPeerAccessAlreadyEnabled = 704 };
+static inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p) { memset(h, 0, sizeof(*h)); memcpy(h->reserved, &p, sizeof(p)); return cudaSuccess; }
+static inline cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t, unsigned) { *p = nullptr; return 1; }   // one process only
+static inline cudaError_t cudaIpcCloseMemHandle(void *) { return cudaSuccess; }
+static inline cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaSuccess; }
 template <typename F>
 static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
 template <typename F>
