@@ -179,26 +179,48 @@ def pinned_array(lib, shape, dtype):
     return np.frombuffer(buf, dtype=dtype).reshape(shape), p
 
 
-def build_fluid(wl, mode, device=0):
-    from equilibrium_b200 import Fluid, FluidConfigs, Rectangle, SimulationConfigs
+def build_fluid(wl, mode, device=0, rank=0, world=1):
+    from equilibrium_b200 import Fluid, FluidConfigs, Rectangle, SimulationConfigs, connect_distributed
     n = wl["size"]
     f = Fluid(FluidConfigs(diffusion=0.0, viscousity=0.001), SimulationConfigs(0.02, wl["k"], n),
-              mode=mode, device=device)
+              mode=mode, device=device, rank=rank, world=world)
+    if world > 1:
+        connect_distributed(f)          # torch.distributed carries the rendezvous blobs, nothing else
     for (x0, y0, x1, y1) in random_rects(n, wl["rects"], wl["seed"]):
         f.fill_obstacle(Rectangle((x0, y0), (x1, y1), n))
     return f
 
 
-def time_device_resident(f, n, steps, warmup, seed):
+def rank_barrier(world):
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.synchronize()
+        dist.barrier()
+
+
+def max_over_ranks(v, world):
+    if world <= 1:
+        return v
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([v], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def time_device_resident(f, n, steps, warmup, seed, world=1):
     imp = impulses(n, warmup + steps, seed)
     f.step_n(warmup, imp[:warmup])
     f.sync()
     timed = [(fr - warmup, x, y, ax, ay) for (fr, x, y, ax, ay) in imp[warmup:]]
+    rank_barrier(world)
     f.timer_start()
     f.step_n(steps, timed)
     ms = f.timer_stop()
     f.sync()
-    return ms
+    rank_barrier(world)
+    return max_over_ranks(ms, world)
 
 
 def main():
@@ -211,6 +233,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip red-black / e2e / cpu legs (profiling runs)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     wl = WORKLOADS[args.workload]
     n, k = wl["size"], wl["k"]
@@ -219,27 +242,27 @@ def main():
         run_reference_arm(args, wl, rank)
         return 0
 
-    if args.gpus > 1 or world > 1:
-        if rank == 0:
-            print(json.dumps({"metric": METRIC, "unit": UNIT, "n_gpus": args.gpus,
-                              "error": "row-slab multi-GPU path not built yet in this round; run with --gpus 1"}))
-        return 0
-
     from equilibrium_b200 import _lib
     lib = _lib.load()
     if lib.eq_device_count() < 1:
         raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
 
     warmup = max(3, args.warmup)
     steps = max(1, args.steps)
     peak, peak_src = measured_peak_gbs()
 
     # ---- exact mode, device-resident (the headline `value`) --------------------------
-    f = build_fluid(wl, "exact")
-    clocks = ClockSampler(0)
-    clocks.start()
-    ms = time_device_resident(f, n, steps, warmup, seed=0)
-    clk = clocks.stop()
+    f = build_fluid(wl, "exact", device=local_rank, rank=rank, world=world)
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    ms = time_device_resident(f, n, steps, warmup, seed=0, world=world)
+    clk = clocks.stop() if rank == 0 else None
     value = n * n * steps / (ms * 1e-3)
 
     # ---- per-phase device times with CUDA events on the launching stream ------------
@@ -248,32 +271,39 @@ def main():
     f.step_n(steps)
     prof = f.profile()
     f.profile_enable(False)
+    rank_barrier(world)
     ls_bytes = 12.0 * prof["lin_solve_cell_iters"]          # R x, R x0, W x per cell-iteration
     ls_s = prof["lin_solve_ms"] * 1e-3
     achieved = ls_bytes / ls_s / 1e9 if ls_s > 0 else 0.0
     launches_per_step = (prof["lin_solve_launches"] + prof["advect_launches"] + prof["project_launches"] +
                          prof["boundary_launches"] + prof["other_launches"]) / max(1, prof["steps"])
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "lin_solve_traffic.json")   # dram bytes per launch from `ncu --set full`
+    if os.path.exists(tp):
+        with open(tp) as fh:
+            traffic = json.load(fh).get(args.workload)
     roofline = {
         "bound": "hbm", "kernel": "k_linsolve_exact (wavefront Gauss-Seidel, all K iterations per launch)",
-        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-        "peak_source": peak_src,
+        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+        "peak_source": peak_src, "per": "GPU (rank 0)" if world > 1 else "GPU",
         "algorithmic_bytes_per_launch": ls_bytes / max(1, prof["lin_solve_launches"]),
         "share_of_step": prof["lin_solve_ms"] / max(1e-9, sum(prof[x] for x in
                          ["lin_solve_ms", "advect_ms", "project_ms", "boundary_ms", "other_ms"])),
-        "step_effective_frac": (algorithmic_bytes_per_cell(k) * value) / 1e9 / peak,
+        "step_effective_frac": (algorithmic_bytes_per_cell(k) * value) / 1e9 / (peak * world),
         "phases_ms_per_step": {x: prof[x] / max(1, prof["steps"]) for x in
                                ["lin_solve_ms", "advect_ms", "project_ms", "boundary_ms", "other_ms"]},
     }
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": steps, "warmup": warmup,
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl_name(wl), "size": n, "gs_iterations": k, "rectangles": wl["rects"],
                    "mode": "exact (bit-identical to the reference's lexicographic Gauss-Seidel)",
                    "cache": "inputs larger than L2 (6 fields x %.0f MiB)" % (n * n * 4 / 2**20)
-                            if n >= 4096 else "L2-resident working set; L2 flushed before the timed region",
-                   "parallelism": "1 GPU"},
+                            if n >= 4096 else "L2-resident working set (the reference's own sizes)",
+                   "parallelism": "1 GPU" if world == 1 else
+                                  f"{world} row slabs, halo rows + solver flags over NVLink peer memory"},
         "roofline": roofline, "clocks": clk, "gpu_launches": int(round(launches_per_step * steps)),
     }
 
@@ -281,43 +311,58 @@ def main():
         # ---- e2e: through the public Fluid API with HOST buffers ------------------------
         # per step: upload the pub fields (density, velocities_x, velocities_y) from pinned
         # host memory, step(), download them back -- the host-mirror drop-in of `pub` Vecs.
-        bufs = [pinned_array(lib, (n, n), np.float32) for _ in range(3)]
+        # (several GPUs: every rank moves the rows of its own slab)
+        r0, r1 = f.owned_rows()
+        rows = r1 - r0
+        bufs = [pinned_array(lib, (rows, n), np.float32) for _ in range(3)]
         names = ["density", "velocities_x", "velocities_y"]
-        for (a, _), nm in zip(bufs, names):
-            f.download(nm, a)
+        fids = [f.FIELDS[nm] for nm in names]
+
+        def down():
+            for (a, _), fid in zip(bufs, fids):
+                _lib.check(lib, lib.eq_download_rows(f._h, fid, r0, rows, a.ctypes.data))
+
+        def up():
+            for (a, _), fid in zip(bufs, fids):
+                _lib.check(lib, lib.eq_upload_rows(f._h, fid, r0, rows, a.ctypes.data))
+
+        down()
         f.sync()
         e2e_steps = max(1, min(steps, 3))
         for it in range(1 + e2e_steps):
             if it == 1:
+                rank_barrier(world)
                 t0 = time.perf_counter()
-            for (a, _), nm in zip(bufs, names):
-                f.upload(nm, a)
+            up()
             f.step()
-            for (a, _), nm in zip(bufs, names):
-                f.download(nm, a)
+            down()
         f.sync()
-        e2e_s = time.perf_counter() - t0
+        rank_barrier(world)
+        e2e_s = max_over_ranks(time.perf_counter() - t0, world)
         line["e2e"] = {"value": n * n * e2e_steps / e2e_s, "unit": UNIT,
                        "h2d_bytes_per_step": 3 * n * n * 4, "d2h_bytes_per_step": 3 * n * n * 4,
                        "ms_per_step": 1e3 * e2e_s / e2e_steps,
-                       "what": "Fluid.upload(pub fields) + Fluid.step() + Fluid.download(pub fields), pinned host buffers, wall clock"}
+                       "what": "upload(pub fields) + Fluid.step() + download(pub fields), pinned host buffers, wall clock"}
         for _, p in bufs:
             lib.eq_host_free(p)
-        f.close()
+    f.close()
 
+    if not args.no_extras and world == 1:
         # ---- red-black fast path on the same workload -----------------------------------
         g = build_fluid(wl, "red_black")
         ms_rb = time_device_resident(g, n, steps, warmup, seed=0)
         line["red_black"] = {"value": n * n * steps / (ms_rb * 1e-3), "unit": UNIT, "ms_per_step": ms_rb / steps,
                              "note": "same K, red-black ordering; tolerance-checked, not bit-exact"}
         g.close()
-
         # ---- CPU baseline beside it -----------------------------------------------------
         line["cpu_baseline"] = cpu_baseline(wl, 1)
-    else:
-        f.close()
 
-    print(json.dumps(line), flush=True)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
     return 0
 
 

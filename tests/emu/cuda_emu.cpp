@@ -2,6 +2,14 @@
 #include "cuda_emu.h"
 
 #include <chrono>
+#include <map>
+#include <mutex>
+#include <string>
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 namespace eq_emu {
 thread_local Ctx ctx;
@@ -113,5 +121,87 @@ cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) {
 }
 cudaError_t cudaEventDestroy(cudaEvent_t e) {
     delete e;
+    return cudaSuccess;
+}
+
+// ---- shared-memory backed "device" allocations + cudaIpc stand-ins ---------------------------
+namespace {
+struct ShmBlock {
+    std::string name;
+    size_t bytes;
+    bool owner;
+};
+std::mutex g_shm_mu;
+std::map<void *, ShmBlock> g_shm;
+unsigned g_shm_counter = 0;
+
+void shm_cleanup() {
+    std::lock_guard<std::mutex> lk(g_shm_mu);
+    for (auto &kv : g_shm)
+        if (kv.second.owner) shm_unlink(kv.second.name.c_str());
+}
+}  // namespace
+
+void *eq_emu_shm_alloc(size_t bytes) {
+    static bool registered = (atexit(shm_cleanup), true);
+    (void)registered;
+    const size_t len = (std::max<size_t>(bytes, 1) + 4095) / 4096 * 4096;
+    std::lock_guard<std::mutex> lk(g_shm_mu);
+    char name[48];
+    snprintf(name, sizeof(name), "/eqemu_%d_%u", (int)getpid(), g_shm_counter++);
+    const int fd = shm_open(name, O_CREAT | O_EXCL | O_RDWR, 0600);
+    if (fd < 0) return nullptr;
+    if (ftruncate(fd, (off_t)len) != 0) {
+        close(fd);
+        shm_unlink(name);
+        return nullptr;
+    }
+    void *p = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (p == MAP_FAILED) {
+        shm_unlink(name);
+        return nullptr;
+    }
+    g_shm[p] = ShmBlock{name, len, true};
+    return p;
+}
+
+void eq_emu_shm_free(void *p) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_shm_mu);
+    auto it = g_shm.find(p);
+    if (it == g_shm.end()) return;
+    munmap(p, it->second.bytes);
+    if (it->second.owner) shm_unlink(it->second.name.c_str());
+    g_shm.erase(it);
+}
+
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p) {
+    std::lock_guard<std::mutex> lk(g_shm_mu);
+    auto it = g_shm.find(p);
+    if (it == g_shm.end()) return 1;
+    memset(h, 0, sizeof(*h));
+    snprintf(h->reserved, 48, "%s", it->second.name.c_str());
+    const uint64_t bytes = it->second.bytes;
+    memcpy(h->reserved + 48, &bytes, 8);
+    return cudaSuccess;
+}
+
+cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned) {
+    uint64_t bytes = 0;
+    memcpy(&bytes, h.reserved + 48, 8);
+    const int fd = shm_open(h.reserved, O_RDWR, 0600);
+    if (fd < 0) return 1;
+    void *m = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (m == MAP_FAILED) return 1;
+    std::lock_guard<std::mutex> lk(g_shm_mu);
+    g_shm[m] = ShmBlock{h.reserved, (size_t)bytes, false};
+    *p = m;
+    return cudaSuccess;
+}
+
+cudaError_t cudaIpcCloseMemHandle(void *p) {
+    eq_emu_shm_free(p);
     return cudaSuccess;
 }

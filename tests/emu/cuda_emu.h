@@ -221,12 +221,16 @@ cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t);
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b);
 cudaError_t cudaEventDestroy(cudaEvent_t e);
+// "device memory" is POSIX shared memory so that another emulated rank (another process) can map
+// it through the cudaIpc* stand-ins below
+void *eq_emu_shm_alloc(size_t bytes);
+void eq_emu_shm_free(void *p);
 template <typename T>
 static inline cudaError_t cudaMalloc(T **p, size_t bytes) {
-    *p = static_cast<T *>(aligned_alloc(128, (bytes + 127) / 128 * 128 + 128));
+    *p = static_cast<T *>(eq_emu_shm_alloc(bytes));
     return *p ? cudaSuccess : 2;
 }
-static inline cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
+static inline cudaError_t cudaFree(void *p) { eq_emu_shm_free(p); return cudaSuccess; }
 static inline cudaError_t cudaMemsetAsync(void *p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
 static inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t) {
     memcpy(d, s, n);
@@ -243,9 +247,9 @@ static inline cudaError_t cudaHostAlloc(void **p, size_t n, unsigned) { *p = mal
 static inline cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
 struct cudaIpcMemHandle_t { char reserved[64]; };
 enum { cudaIpcMemLazyEnablePeerAccess = 1, cudaErrorPeerAccessAlreadyEnabled = 704 };
-static inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p) { memset(h, 0, sizeof(*h)); memcpy(h->reserved, &p, sizeof(p)); return cudaSuccess; }
-static inline cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t, unsigned) { *p = nullptr; return 1; }   // one process only
-static inline cudaError_t cudaIpcCloseMemHandle(void *) { return cudaSuccess; }
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p);
+cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned flags);
+cudaError_t cudaIpcCloseMemHandle(void *p);
 static inline cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaSuccess; }
 template <typename F>
 static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
