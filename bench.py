@@ -347,13 +347,15 @@ def main():
             lib.eq_host_free(p)
     f.close()
 
-    if not args.no_extras and world == 1:
-        # ---- red-black fast path on the same workload -----------------------------------
-        g = build_fluid(wl, "red_black")
-        ms_rb = time_device_resident(g, n, steps, warmup, seed=0)
+    if not args.no_extras:
+        # ---- red-black fast path on the same workload (same slabs when world > 1) --------
+        g = build_fluid(wl, "red_black", device=local_rank, rank=rank, world=world)
+        ms_rb = time_device_resident(g, n, steps, warmup, seed=0, world=world)
         line["red_black"] = {"value": n * n * steps / (ms_rb * 1e-3), "unit": UNIT, "ms_per_step": ms_rb / steps,
+                             "n_gpus": world,
                              "note": "same K, red-black ordering; tolerance-checked, not bit-exact"}
         g.close()
+    if not args.no_extras and world == 1:
         # ---- CPU baseline beside it -----------------------------------------------------
         line["cpu_baseline"] = cpu_baseline(wl, 1)
 

@@ -314,8 +314,20 @@ struct LinSolveReq {
     float a, c;
 };
 
+// Iterations are handed out in groups of `kgroup`: inside a group jobs go in wavefront order
+// w = b + 2(k - k0) (a job depends only on w-1, or on the previous group).  One group = every
+// iteration is the plain wavefront; small groups let the sweep reach the last band of a slab
+// early, which is what lets the next GPU start (pipeline over groups).
+static int job_group_size(const eq_fluid *h, int kc) {
+    if (const char *e = getenv("EQ_LSX_KGROUP")) return std::max(1, std::min(kc, atoi(e)));
+    if (h->world <= 1) return kc;
+    return std::max(1, std::min(kc, (kc + 2 * h->world - 1) / (2 * h->world) + 1));
+}
+
 static int get_job_table(eq_fluid *h, int kc, const uint32_t **out) {
-    auto it = h->job_tables->find(kc);
+    const int G = job_group_size(h, kc);
+    const int key = kc * 1024 + G;
+    auto it = h->job_tables->find(key);
     if (it != h->job_tables->end()) {
         *out = it->second;
         return EQ_OK;
@@ -323,19 +335,21 @@ static int get_job_table(eq_fluid *h, int kc, const uint32_t **out) {
     const int NB = (h->L.N - 2 + 31) / 32;
     std::vector<uint32_t> tab;
     tab.reserve((size_t)kc * (h->b_hi - h->b_lo));
-    // wavefront order: w = b + 2k ascending; a job depends only on w-1.  A rank lists
-    // only the bands of its slab; every rank uses the same global order, so cross-GPU waits also
-    // point at jobs that were handed out earlier on their own GPU.
-    for (int w = 0; w <= (NB - 1) + 2 * (kc - 1); ++w)
-        for (int k = 0; k < kc; ++k) {
-            const int b = w - 2 * k;
-            if (b >= h->b_lo && b < h->b_hi) tab.push_back(((uint32_t)k << 16) | (uint32_t)b);
-        }
+    // A rank lists only the bands of its slab; every rank uses the same global order, so cross-GPU
+    // waits also point at jobs that were handed out earlier on their own GPU.
+    for (int k0 = 0; k0 < kc; k0 += G) {
+        const int k1 = std::min(kc, k0 + G);
+        for (int w = 0; w <= (NB - 1) + 2 * (k1 - k0 - 1); ++w)
+            for (int k = k0; k < k1; ++k) {
+                const int b = w - 2 * (k - k0);
+                if (b >= h->b_lo && b < h->b_hi) tab.push_back(((uint32_t)k << 16) | (uint32_t)b);
+            }
+    }
     uint32_t *d = nullptr;
     CU(cudaMalloc(&d, tab.size() * sizeof(uint32_t)));
     CU(cudaMemcpyAsync(d, tab.data(), tab.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));   // `tab` is pageable and goes out of scope
-    (*h->job_tables)[kc] = d;
+    (*h->job_tables)[key] = d;
     *out = d;
     return EQ_OK;
 }
