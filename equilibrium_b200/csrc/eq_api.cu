@@ -73,6 +73,7 @@ struct eq_fluid {
     int sm_count;
     cudaStream_t own_stream, stream;
     float *f[6];            // EQ_F_DENSITY .. EQ_F_SCRATCH
+    float *rb_tmp;          // ping-pong partner of x in the tiled red-black solver
     uint8_t *cells;
     // mask-derived tables (rebuilt lazily when the mask changed)
     uint8_t *codes, *row_fluid, *col_fluid, *chunk_flags;
@@ -107,6 +108,7 @@ struct eq_fluid {
     int b_lo, b_hi;                              // owned bands of the wavefront solver
     float *peer_f[EQ_MAX_RANKS][6];              // every rank's fields / raw streams / flags / sync slots
     float *peer_raw[EQ_MAX_RANKS][2];
+    float *peer_tmp[EQ_MAX_RANKS];
     unsigned *peer_flags[EQ_MAX_RANKS];
     unsigned *peer_sync[EQ_MAX_RANKS];
     bool peer_ipc[EQ_MAX_RANKS];                 // mapped with cudaIpcOpenMemHandle (must be closed)
@@ -187,25 +189,33 @@ static int need_attached(eq_fluid *h) {
     return EQ_OK;
 }
 
-// refresh the ghost rows of `field` on both neighbours and mine from theirs
-static int halo_xchg(eq_fluid *h, float *field) {
-    if (h->world <= 1) return EQ_OK;
-    TRY(need_attached(h));
-    const int fi = field_index(h, field);
-    if (fi < 0) return eq_fail(EQ_ERR_INVALID, "halo exchange of an unknown field");
+// refresh the ghost rows of a buffer on both neighbours and mine from theirs
+static int halo_xchg_buf(eq_fluid *h, float *buf, float *up, float *down, int nrows) {
     ProfScope ps(h, CAT_OTHER, 1);
     EqHaloArgs a;
     memset(&a, 0, sizeof(a));
-    a.field = field;
-    a.peer_up = h->rank > 0 ? h->peer_f[h->rank - 1][fi] : nullptr;
-    a.peer_down = h->rank + 1 < h->world ? h->peer_f[h->rank + 1][fi] : nullptr;
+    a.field = buf;
+    a.peer_up = up;
+    a.peer_down = down;
     a.sync = h->sync;
     a.sync_up = h->rank > 0 ? h->peer_sync[h->rank - 1] : nullptr;
     a.sync_down = h->rank + 1 < h->world ? h->peer_sync[h->rank + 1] : nullptr;
     a.epoch = ++h->halo_epoch;
+    a.nrows = nrows;
     a.error = reinterpret_cast<int *>(h->flags + 1);
     EQ_LAUNCH(k_halo_exchange, 2, 1024, 16, h->stream, a, h->L);
     return check_launch("k_halo_exchange");
+}
+
+static int halo_xchg(eq_fluid *h, float *field, int nrows = 1) {
+    if (h->world <= 1) return EQ_OK;
+    TRY(need_attached(h));
+    const bool up = h->rank > 0, down = h->rank + 1 < h->world;
+    if (field == h->rb_tmp)
+        return halo_xchg_buf(h, field, up ? h->peer_tmp[h->rank - 1] : nullptr, down ? h->peer_tmp[h->rank + 1] : nullptr, nrows);
+    const int fi = field_index(h, field);
+    if (fi < 0) return eq_fail(EQ_ERR_INVALID, "halo exchange of an unknown field");
+    return halo_xchg_buf(h, field, up ? h->peer_f[h->rank - 1][fi] : nullptr, down ? h->peer_f[h->rank + 1][fi] : nullptr, nrows);
 }
 
 // every rank has finished what it launched so far
@@ -442,29 +452,28 @@ static int lin_solve_exact(eq_fluid *h, const LinSolveReq *req, int nreq, int64_
 
 static int lin_solve_red_black(eq_fluid *h, const LinSolveReq *req, int nreq, int64_t iters) {
     const EqLayout L = h->L;
-    const int threads = 256;
-    const dim3 grid((unsigned)((L.N / 2 + threads) / threads), (unsigned)owned_interior_rows(h), 1);
-    for (int64_t k = 0; k < iters; ++k) {
-        for (int i = 0; i < nreq; ++i) {
-            const float c_recip = 1.0f / req[i].c;
-            TRY(halo_xchg(h, req[i].x));            // each colour reads the other colour's ghost rows
-            EQ_LAUNCH(k_rb_half, grid, threads, 0, h->stream, req[i].x, req[i].x0, req[i].a, c_recip, 0, L);
-            TRY(halo_xchg(h, req[i].x));
-            EQ_LAUNCH(k_rb_half, grid, threads, 0, h->stream, req[i].x, req[i].x0, req[i].a, c_recip, 1, L);
-            TRY(check_launch("k_rb_half"));
-            if (req[i].orient == EQ_ADJUST_COLUMN) TRY(halo_xchg(h, req[i].x));
-            // fused into the same category: the boundary pass is part of the iteration
-            if (req[i].orient == EQ_PASSIVE) {
-                EQ_LAUNCH(k_bnd_passive, (L.N + 255) / 256, 256, 0, h->stream, req[i].x, h->row_fluid, h->col_fluid, L);
-            } else {
-                const uint2 *list = req[i].orient == EQ_ADJUST_ROW ? h->row_list : h->col_list;
-                const unsigned n = req[i].orient == EQ_ADJUST_ROW ? h->n_row : h->n_col;
-                EQ_LAUNCH(k_bnd_list, std::max(1u, (n + 255u) / 256u), 256, 0, h->stream, req[i].x, list, n, L);
-            }
-            TRY(check_launch("boundary in red-black"));
+    const int rows = L.row1 - L.row0;
+    const dim3 grid((unsigned)((L.N + RB_TW - 1) / RB_TW), (unsigned)((rows + RB_TH - 1) / RB_TH), 1);
+    for (int i = 0; i < nreq; ++i) {
+        const float c_recip = 1.0f / req[i].c;
+        float *cur = req[i].x, *other = h->rb_tmp;
+        // tiles at a slab edge recompute RB_H rows of the neighbour: they need its x0 there
+        TRY(halo_xchg(h, const_cast<float *>(req[i].x0), RB_H));
+        for (int64_t done = 0; done < iters; done += RB_T) {
+            const int it = (int)std::min<int64_t>(RB_T, iters - done);
+            TRY(halo_xchg(h, cur, RB_H));
+            EQ_LAUNCH(k_rb_tiled, grid, RB_THREADS, RB_SMEM_BYTES, h->stream, cur, other, req[i].x0, h->codes,
+                      h->row_fluid, h->col_fluid, req[i].a, c_recip, req[i].orient, it, L.row0, L.row1, L);
+            TRY(check_launch("k_rb_tiled"));
+            std::swap(cur, other);
         }
+        if (cur != req[i].x)
+            CU(cudaMemcpyAsync(req[i].x + (size_t)L.row0 * L.P, cur + (size_t)L.row0 * L.P,
+                               (size_t)rows * L.P * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+        EQ_LAUNCH(k_corners, 1, 32, 0, h->stream, req[i].x, L);
+        TRY(check_launch("k_corners"));
+        TRY(halo_xchg(h, req[i].x));
     }
-    for (int i = 0; i < nreq; ++i) TRY(halo_xchg(h, req[i].x));
     return EQ_OK;
 }
 
@@ -474,7 +483,7 @@ static int lin_solve(eq_fluid *h, const LinSolveReq *req, int nreq, int64_t iter
     const int64_t cells = (int64_t)(h->L.N - 2) * owned_interior_rows(h);
     h->prof_cell_iters += cells * iters * nreq;
     if (h->prm.mode == EQ_MODE_RED_BLACK) {
-        ProfScope ps(h, CAT_LS, (int)(3 * iters * nreq));
+        ProfScope ps(h, CAT_LS, (int)(((iters + RB_T - 1) / RB_T + 1) * nreq));
         return lin_solve_red_black(h, req, nreq, iters);
     }
     ProfScope ps(h, CAT_LS, (int)((iters + LSX_KMAX - 1) / LSX_KMAX) + nreq);
@@ -621,6 +630,8 @@ static int alloc_handle(const EqParams *params, eq_fluid **out) {
         CU(cudaMalloc(&h->f[i], elems * sizeof(float)));
         CU(cudaMemsetAsync(h->f[i], 0, elems * sizeof(float), h->stream));
     }
+    CU(cudaMalloc(&h->rb_tmp, elems * sizeof(float)));
+    CU(cudaMemsetAsync(h->rb_tmp, 0, elems * sizeof(float), h->stream));
     CU(cudaMalloc(&h->cells, elems));
     CU(cudaMemsetAsync(h->cells, 0, elems, h->stream));
     CU(cudaMalloc(&h->codes, elems));
@@ -643,8 +654,10 @@ static int alloc_handle(const EqParams *params, eq_fluid **out) {
     h->peer_raw[h->rank][0] = h->raw[0];
     h->peer_raw[h->rank][1] = h->raw[1];
     h->peer_flags[h->rank] = h->flags;
+    h->peer_tmp[h->rank] = h->rb_tmp;
     h->peer_sync[h->rank] = h->sync;
     CU(cudaFuncSetAttribute(k_linsolve_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LSX_SMEM_BYTES));
+    CU(cudaFuncSetAttribute(k_rb_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RB_SMEM_BYTES));
     int per_sm = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_linsolve_exact, LSX_THREADS, LSX_SMEM_BYTES));
     h->lsx_ctas = std::max(1, per_sm) * h->sm_count;
@@ -719,6 +732,7 @@ int eq_destroy(eq_fluid *h) {
     if (h->own_stream) cudaStreamSynchronize(h->own_stream);
     for (int i = 0; i < 6; ++i) cudaFree(h->f[i]);
     cudaFree(h->cells);
+    cudaFree(h->rb_tmp);
     cudaFree(h->codes);
     cudaFree(h->row_fluid);
     cudaFree(h->col_fluid);
@@ -738,6 +752,7 @@ int eq_destroy(eq_fluid *h) {
             cudaIpcCloseMemHandle(h->peer_raw[r][1]);
             cudaIpcCloseMemHandle(h->peer_flags[r]);
             cudaIpcCloseMemHandle(h->peer_sync[r]);
+            cudaIpcCloseMemHandle(h->peer_tmp[r]);
         }
     cudaFree(h->flags);
     cudaFree(h->sync);
@@ -1200,7 +1215,7 @@ int eq_l2_flush(eq_fluid *h) {
 // Each rank exports one blob; the launcher gathers them (torch.distributed / any side channel)
 // and hands every rank the concatenation.  Peers in other processes are mapped with CUDA IPC,
 // peers in the same process (several handles, one per device) with plain peer access.
-#define EQ_IPC_ITEMS 10
+#define EQ_IPC_ITEMS 11
 struct EqIpcBlob {
     uint32_t magic, rank, world, size;
     int32_t device, pad;
@@ -1215,6 +1230,7 @@ static void ipc_items(eq_fluid *h, void *items[EQ_IPC_ITEMS]) {
     items[7] = h->raw[1];
     items[8] = h->flags;
     items[9] = h->sync;
+    items[10] = h->rb_tmp;
 }
 
 int eq_ipc_blob_bytes(void) { return (int)sizeof(EqIpcBlob); }
@@ -1272,6 +1288,7 @@ int eq_ipc_attach(eq_fluid *h, const void *blobs, size_t blob_bytes, int world) 
         h->peer_raw[r][1] = static_cast<float *>(mapped[7]);
         h->peer_flags[r] = static_cast<unsigned *>(mapped[8]);
         h->peer_sync[r] = static_cast<unsigned *>(mapped[9]);
+        h->peer_tmp[r] = static_cast<float *>(mapped[10]);
     }
     h->attached = true;
     return EQ_OK;

@@ -17,6 +17,7 @@ struct EqHaloArgs {
     unsigned *sync;               // my slots, written by the neighbours
     unsigned *sync_up, *sync_down;// the neighbours' slots
     unsigned epoch;
+    int nrows;                    // boundary rows pushed each way (1 for the stencils, 3T for tiled red-black)
     int *error;
 };
 
@@ -56,10 +57,10 @@ __global__ void __launch_bounds__(1024) k_halo_exchange(EqHaloArgs a, EqLayout L
     }
     __syncthreads();
     if (!ok) return;
-    const int row = dir == 0 ? L.row0 : L.row1 - 1;       // first / last owned row
+    const int row = dir == 0 ? L.row0 : L.row1 - a.nrows;  // first / last owned rows
     const float4 *src = reinterpret_cast<const float4 *>(a.field + (size_t)row * L.P);
     float4 *dst = reinterpret_cast<float4 *>(peer + (size_t)row * L.P);
-    for (int i = threadIdx.x; i < L.P / 4; i += blockDim.x) dst[i] = src[i];
+    for (int i = threadIdx.x; i < a.nrows * (L.P / 4); i += blockDim.x) dst[i] = src[i];
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence_system();

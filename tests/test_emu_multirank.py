@@ -108,8 +108,9 @@ def test_lin_solve_across_two_slabs(oracle, emu_lib, orient):
     assert P.bits_equal(got, x), P.describe_diff(got, x)
 
 
-def test_red_black_across_slabs_matches_its_restatement(oracle, emu_lib):
-    n, k, world = 96, 3, 2
+@pytest.mark.parametrize("n,k", [(96, 3), (200, 6)])
+def test_red_black_across_slabs_matches_its_restatement(oracle, emu_lib, n, k):
+    world = 2
     rects = [(10, 40, 60, 70)]
     fluids = make_rank_fluids(emu_lib, world, n, k, rects, mode="red_black")
     ref = oracle.RefFluid(n, 0.02, k)

@@ -107,3 +107,19 @@ def test_red_black_close_to_oracle_red_black(oracle, emu_lib):
         oracle.lin_solve(orient, x, x0, 0.37, 2.48, k, ref.cells, red_black=True)
         got = dev.download("velocities_x")
         assert P.bits_equal(got, x), P.describe_diff(got, x)
+
+
+@pytest.mark.parametrize("orient", [P.ROW, P.COL, P.PASSIVE])
+def test_red_black_tiled_across_tiles(oracle, emu_lib, orient):
+    # 200 > one 128 x 64 tile in both directions; 5 iterations = one full pass of 4 plus a tail of 1
+    rng = np.random.default_rng(1)
+    n, k = 200, 5
+    dev, ref = P.make_pair(oracle, emu_lib, n, k, [(60, 50, 140, 70), (120, 100, 131, 190), (1, 128, 40, 129)],
+                           mode="red_black")
+    x, x0 = P.rnd(rng, n), P.rnd(rng, n)
+    dev.upload("velocities_x", x)
+    dev.upload("velocities_x0", x0)
+    dev.op_lin_solve(orient, "velocities_x", "velocities_x0", 0.37, 2.48, k)
+    oracle.lin_solve(orient, x, x0, 0.37, 2.48, k, ref.cells, red_black=True)
+    got = dev.download("velocities_x")
+    assert P.bits_equal(got, x), P.describe_diff(got, x)
