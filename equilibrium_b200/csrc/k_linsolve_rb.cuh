@@ -5,7 +5,7 @@
 // restatement in the oracle and tolerance-checked against the lexicographic one
 // (tests/test_red_black.py).
 //
-// k_rb_tiled: temporally blocked.  A CTA stages a (TW+2h) x (TH+2h) region of x, x0 and the
+// k_rb_tiled: temporally blocked.  A CTA stages a (TW+2h) x (TH+2h) region (152 x 80 cells) of x, x0 and the
 // fix-up codes in shared memory, runs RB_T complete iterations (red, black, boundary fix-up) on
 // it and writes the central TW x TH cells: x and x0 cross HBM once per RB_T iterations instead
 // of twice per iteration.  Cells near the region edge go stale by 3 cells per iteration (red
@@ -18,10 +18,12 @@
 #define RB_T 4
 #define RB_H (3 * RB_T)
 #define RB_TW 128
-#define RB_TH 64
+#define RB_TH 56
 #define RB_RW (RB_TW + 2 * RB_H)      // 152
-#define RB_RH (RB_TH + 2 * RB_H)      // 88
-#define RB_THREADS 512
+#define RB_RH (RB_TH + 2 * RB_H)      // 80: two CTAs (109 KB each) fit one SM
+#define RB_THREADS 532                 // 7 row phases x 76 column pairs; also 14 rows x 38 quads for staging
+#define RB_HW (RB_RW / 2)               // column pairs per row
+#define RB_RW4 (RB_RW / 4)              // 4-cell groups per row
 #define RB_SMEM_BYTES (RB_RW * RB_RH * 9)
 
 // v1 kernel, kept for the tail (iterations % RB_T) and as the simplest statement of the sweep:
@@ -51,59 +53,75 @@ __global__ void __launch_bounds__(RB_THREADS) k_rb_tiled(const float *__restrict
     const int gx0 = (int)blockIdx.x * RB_TW - RB_H;              // global coordinates of region cell (0,0)
     const int gy0 = row_lo + (int)blockIdx.y * RB_TH - RB_H;
     // ---- stage the region (cells outside the grid are never touched) ----
-    for (int p = threadIdx.x; p < RB_RW * RB_RH; p += RB_THREADS) {
-        const int ly = p / RB_RW, lx = p - ly * RB_RW;
-        const int gx = gx0 + lx, gy = gy0 + ly;
-        float v = 0.f, v0 = 0.f;
-        uint8_t c = EQ_CODE_WALL;
-        if (gx >= 0 && gx < N && gy >= 0 && gy < N) {
-            const size_t o = (size_t)gx + (size_t)gy * P;
-            v = xin[o];
-            v0 = x0[o];
-            c = codes[o];
+    unsigned any_code = 0;
+    for (int ly = threadIdx.x / RB_RW4; ly < RB_RH; ly += RB_THREADS / RB_RW4) {
+        // RB_RW4 threads per row, each stages 4 consecutive cells (scalar loads: gx0 is not 16-byte aligned)
+        const int lx4 = (threadIdx.x % RB_RW4) * 4;
+        const int gy = gy0 + ly;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int lx = lx4 + u, gx = gx0 + lx;
+            float v = 0.f, v0 = 0.f;
+            uint8_t c = EQ_CODE_WALL;
+            if (gx >= 0 && gx < N && gy >= 0 && gy < N) {
+                const size_t o = (size_t)gx + (size_t)gy * P;
+                v = xin[o];
+                v0 = x0[o];
+                c = codes[o];
+            }
+            const int p = ly * RB_RW + lx;
+            xs[p] = v;
+            x0s[p] = v0;
+            cs[p] = c;
+            any_code |= c & 15u;
         }
-        xs[p] = v;
-        x0s[p] = v0;
-        cs[p] = c;
     }
-    __syncthreads();
-    const int HW = RB_RW / 2;
+    // does this region contain anything the boundary pass has to touch?
+    const bool fix_rc = __syncthreads_or((int)any_code) != 0;
+    const bool fix_passive = (gx0 <= 0) || (gy0 <= 0) || (gx0 + RB_RW >= N) || (gy0 + RB_RH >= N);
+    // thread -> (column pair, row phase): no divisions inside the sweeps
+    const int cp = threadIdx.x % RB_HW, ry = threadIdx.x / RB_HW;
+    constexpr int RSTEP = RB_THREADS / RB_HW;                       // rows advanced per pass of the row loop
     for (int it = 0; it < iters; ++it) {
         for (int colour = 0; colour < 2; ++colour) {
             // interior cells of the region (all four neighbours staged) that are interior cells of the grid
-            for (int p = threadIdx.x; p < HW * (RB_RH - 2); p += RB_THREADS) {
-                const int ly = 1 + p / HW;
-                const int gy = gy0 + ly;
-                int lx = 2 * (p % HW) + ((colour ^ gy ^ gx0) & 1);
-                if (lx == 0) lx = -1;                         // column 0 of the region has no left neighbour
-                const int gx = gx0 + lx;
-                if (lx >= 1 && lx <= RB_RW - 2 && gx >= 1 && gx <= N - 2 && gy >= 1 && gy <= N - 2) {
-                    const int o = ly * RB_RW + lx;
-                    xs[o] = gs_update(x0s[o], xs[o + 1], xs[o - 1], xs[o + RB_RW], xs[o - RB_RW], a, c_recip);
+            if (ry < RSTEP) {
+#pragma unroll 4
+                for (int ly = 1 + ry; ly <= RB_RH - 2; ly += RSTEP) {
+                    const int gy = gy0 + ly;
+                    const int lx = 2 * cp + ((colour ^ gy ^ gx0) & 1);
+                    const int gx = gx0 + lx;
+                    if (lx >= 1 && lx <= RB_RW - 2 && gx >= 1 && gx <= N - 2 && gy >= 1 && gy <= N - 2) {
+                        const int o = ly * RB_RW + lx;
+                        xs[o] = gs_update(x0s[o], xs[o + 1], xs[o - 1], xs[o + RB_RW], xs[o - RB_RW], a, c_recip);
+                    }
                 }
             }
             __syncthreads();
         }
         // ---- set_boundaries (fluid.rs:252-272) inside the region ----
         if (orient == EQ_PASSIVE) {
-            // frame cells copy their interior neighbour (fluid.rs:182-186, conditional per quirk Q6)
-            for (int p = threadIdx.x; p < RB_RW * RB_RH; p += RB_THREADS) {
-                const int ly = p / RB_RW, lx = p - ly * RB_RW;
-                const int gx = gx0 + lx, gy = gy0 + ly;
-                if (gx < 0 || gx >= N || gy < 0 || gy >= N) continue;
-                const bool fx = (gx == 0 || gx == N - 1), fy = (gy == 0 || gy == N - 1);
-                if (fx == fy) continue;                       // interior cell or corner
-                if (fy) {
-                    if (gx >= 1 && gx <= N - 2 && col_fluid[gx]) {
-                        const int src = (gy == 0) ? p + RB_RW : p - RB_RW;
-                        if (src >= 0 && src < RB_RW * RB_RH) xs[p] = xs[src];
+            if (fix_passive) {
+                // frame cells copy their interior neighbour (fluid.rs:182-186, conditional per quirk Q6)
+                for (int p = threadIdx.x; p < RB_RW * RB_RH; p += RB_THREADS) {
+                    const int ly = p / RB_RW, lx = p - ly * RB_RW;
+                    const int gx = gx0 + lx, gy = gy0 + ly;
+                    if (gx < 0 || gx >= N || gy < 0 || gy >= N) continue;
+                    const bool fx = (gx == 0 || gx == N - 1), fy = (gy == 0 || gy == N - 1);
+                    if (fx == fy) continue;                       // interior cell or corner
+                    if (fy) {
+                        if (gx >= 1 && gx <= N - 2 && col_fluid[gx]) {
+                            const int src = (gy == 0) ? p + RB_RW : p - RB_RW;
+                            if (src >= 0 && src < RB_RW * RB_RH) xs[p] = xs[src];
+                        }
+                    } else if (gy >= 1 && gy <= N - 2 && row_fluid[gy]) {
+                        const int sl = (gx == 0) ? lx + 1 : lx - 1;
+                        if (sl >= 0 && sl < RB_RW) xs[p] = xs[ly * RB_RW + sl];
                     }
-                } else if (gy >= 1 && gy <= N - 2 && row_fluid[gy]) {
-                    const int sl = (gx == 0) ? lx + 1 : lx - 1;
-                    if (sl >= 0 && sl < RB_RW) xs[p] = xs[ly * RB_RW + sl];
                 }
+                __syncthreads();
             }
-        } else {
+        } else if (fix_rc) {
             const unsigned shift = (orient == EQ_ADJUST_ROW) ? 0u : 2u;
             for (int p = threadIdx.x; p < RB_RW * RB_RH; p += RB_THREADS) {
                 const unsigned code = (cs[p] >> shift) & 3u;
@@ -121,8 +139,8 @@ __global__ void __launch_bounds__(RB_THREADS) k_rb_tiled(const float *__restrict
                 }
                 xs[p] = -xs[src];                              // sources are wall cells: never a destination
             }
+            __syncthreads();
         }
-        __syncthreads();
     }
     // ---- write the centre ----
     for (int p = threadIdx.x; p < RB_TW * RB_TH; p += RB_THREADS) {

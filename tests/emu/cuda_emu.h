@@ -51,6 +51,7 @@ struct BlockState {
     std::barrier<> bar;
     std::vector<std::unique_ptr<WarpState>> warps;
     std::vector<unsigned char> dyn_smem;
+    std::atomic<int> or_acc{0};
     explicit BlockState(int n) : bar(n) {}
 };
 struct Ctx {
@@ -82,6 +83,16 @@ static inline void __syncwarp(unsigned = 0xffffffffu) {
 }
 static inline void __syncthreads() {
     if (eq_emu::ctx.block) eq_emu::ctx.block->bar.arrive_and_wait();
+}
+static inline int __syncthreads_or(int v) {
+    eq_emu::BlockState *b = eq_emu::ctx.block;
+    if (v) b->or_acc.fetch_or(1);
+    b->bar.arrive_and_wait();
+    const int r = b->or_acc.load();
+    b->bar.arrive_and_wait();
+    b->or_acc.store(0);
+    b->bar.arrive_and_wait();
+    return r;
 }
 template <typename T>
 static inline T eq_emu_exchange(T v, int src_lane) {
