@@ -277,16 +277,21 @@ def main():
     achieved = ls_bytes / ls_s / 1e9 if ls_s > 0 else 0.0
     launches_per_step = (prof["lin_solve_launches"] + prof["advect_launches"] + prof["project_launches"] +
                          prof["boundary_launches"] + prof["other_launches"]) / max(1, prof["steps"])
+    # lin_solve_launches counts the wavefront launches plus one tiny corner kernel per solved field
+    wave_launches = max(1, prof["lin_solve_launches"] - 5 * prof["steps"])
     traffic = None
     tp = os.path.join(ROOT, "profiles", "lin_solve_traffic.json")   # dram bytes per launch from `ncu --set full`
-    if os.path.exists(tp):
+    if os.path.exists(tp) and world == 1:
         with open(tp) as fh:
-            traffic = json.load(fh).get(args.workload)
+            rec = json.load(fh).get(args.workload)
+        if rec:   # per launch like `achieved`: one launch solves 1 or 2 fields (5 solves in 4 launches per frame)
+            traffic = rec["dram_bytes_per_solve"] * 5.0 * prof["steps"] / wave_launches
     roofline = {
         "bound": "hbm", "kernel": "k_linsolve_exact (wavefront Gauss-Seidel, all K iterations per launch)",
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
         "peak_source": peak_src, "per": "GPU (rank 0)" if world > 1 else "GPU",
-        "algorithmic_bytes_per_launch": ls_bytes / max(1, prof["lin_solve_launches"]),
+        "algorithmic_bytes_per_launch": ls_bytes / wave_launches,
+        "launch_ms": prof["lin_solve_ms"] / wave_launches,
         "share_of_step": prof["lin_solve_ms"] / max(1e-9, sum(prof[x] for x in
                          ["lin_solve_ms", "advect_ms", "project_ms", "boundary_ms", "other_ms"])),
         "step_effective_frac": (algorithmic_bytes_per_cell(k) * value) / 1e9 / (peak * world),
