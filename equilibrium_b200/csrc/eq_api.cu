@@ -15,6 +15,7 @@
 
 #include "eq_common.cuh"
 #include "k_linsolve_exact.cuh"
+#include "k_linsolve_tb.cuh"
 #include "k_linsolve_rb.cuh"
 #include "k_stencils.cuh"
 #include "k_multigpu.cuh"
@@ -24,6 +25,11 @@
 // ---------------------------------------------------------------------------
 // errors
 // ---------------------------------------------------------------------------
+static int env_int(const char *name, int dflt) {
+    const char *e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
 static thread_local char g_err[512] = "";
 
 static int eq_fail(int code, const char *fmt, ...) {
@@ -76,8 +82,11 @@ struct eq_fluid {
     float *rb_tmp;          // ping-pong partner of x in the tiled red-black solver
     uint8_t *cells;
     // mask-derived tables (rebuilt lazily when the mask changed)
-    uint8_t *codes, *row_fluid, *col_fluid, *chunk_flags;
+    uint8_t *codes, *row_fluid, *col_fluid, *chunk_flags, *chunk_flags_tb;
+    float *tb_raw[2], *tb_edge[2];   // side streams of the temporally blocked solver
+    int tb_ctas;
     unsigned *counts;       // [4] device
+    bool all_cols_fluid;
     uint2 *row_list, *col_list;
     unsigned n_row, n_col;
     size_t cap_row, cap_col;
@@ -266,12 +275,19 @@ static int ensure_tables(eq_fluid *h) {
     CU(cudaMemsetAsync(h->row_fluid, 0, L.N, h->stream));
     CU(cudaMemsetAsync(h->col_fluid, 0, L.P, h->stream));
     CU(cudaMemsetAsync(h->chunk_flags, 0, 2 * (size_t)((L.N - 2 + 31) / 32) * ((L.N + EQ_LSX_CW - 1) / EQ_LSX_CW), h->stream));
+    CU(cudaMemsetAsync(h->chunk_flags_tb, 0, 2 * (size_t)((L.N - 2 + TBX_SK + 31) / 32) * ((L.N + EQ_LSX_CW - 1) / EQ_LSX_CW), h->stream));
     EQ_LAUNCH(k_build_codes, row_grid(h, L.N), 256, 0, h->stream, h->cells, h->codes, h->row_fluid, h->col_fluid,
-              h->chunk_flags, h->counts, nullptr, nullptr, 0, L);
+              h->chunk_flags, h->chunk_flags_tb, h->counts, nullptr, nullptr, 0, L);
     TRY(check_launch("k_build_codes"));
     unsigned counts[4];
     CU(cudaMemcpyAsync(counts, h->counts, sizeof(counts), cudaMemcpyDeviceToHost, h->stream));
+    std::vector<uint8_t> colf((size_t)L.N);
+    CU(cudaMemcpyAsync(colf.data(), h->col_fluid, (size_t)L.N, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
+    // every interior column holds a NoWall cell (anything but an obstacle spanning the full height): the Passive
+    // frame-row copies of quirk Q6 are then unconditional and the wavefront solver keeps its fast loop for them
+    h->all_cols_fluid = true;
+    for (int i = 1; i <= L.N - 2; ++i) h->all_cols_fluid = h->all_cols_fluid && colf[(size_t)i] != 0;
     if (counts[0] > h->cap_row) {
         if (h->row_list) CU(cudaFree(h->row_list));
         h->row_list = nullptr;
@@ -285,7 +301,7 @@ static int ensure_tables(eq_fluid *h) {
         CU(cudaMalloc(&h->col_list, h->cap_col * sizeof(uint2)));
     }
     EQ_LAUNCH(k_build_codes, row_grid(h, L.N), 256, 0, h->stream, h->cells, h->codes, h->row_fluid, h->col_fluid,
-              h->chunk_flags, h->counts, h->row_list, h->col_list, 1, L);
+              h->chunk_flags, h->chunk_flags_tb, h->counts, h->row_list, h->col_list, 1, L);
     TRY(check_launch("k_build_codes(lists)"));
     h->n_row = counts[0];
     h->n_col = counts[1];
@@ -415,6 +431,7 @@ static int lin_solve_exact(eq_fluid *h, const LinSolveReq *req, int nreq, int64_
         p.error = reinterpret_cast<int *>(h->flags + 1);
         p.stats = h->lsx_stats;
         p.debug_nodeps = getenv("EQ_LSX_NODEPS") ? 1 : 0;
+        p.rotate_roles = env_int("EQ_LSX_ROT", 1);
         p.slack = getenv("EQ_LSX_SLACK") ? atoi(getenv("EQ_LSX_SLACK")) : 0;
         p.trace = h->lsx_trace;
         p.jobtimes = nullptr;
@@ -441,6 +458,86 @@ static int lin_solve_exact(eq_fluid *h, const LinSolveReq *req, int nreq, int64_
         // ... and afterwards it waits until the neighbour's solver (which patches my last row and
         // publishes into my mirrors until its very end) is done, then refreshes the ghost rows.
         for (int i = 0; i < nreq; ++i) TRY(halo_xchg(h, req[i].x));
+        done += kc;
+    }
+    for (int i = 0; i < nreq; ++i) {
+        EQ_LAUNCH(k_corners, 1, 32, 0, h->stream, req[i].x, L);
+        TRY(check_launch("k_corners"));
+    }
+    return EQ_OK;
+}
+
+// Temporally blocked variant (k_linsolve_tb.cuh): TBX_T iterations per job.  Single GPU.
+static int get_tb_job_table(eq_fluid *h, int G, const uint32_t **out) {
+    const int key = -G;   // shares the cache with the plain tables (their keys are positive)
+    auto it = h->job_tables->find(key);
+    if (it != h->job_tables->end()) {
+        *out = it->second;
+        return EQ_OK;
+    }
+    const int NBP = (h->L.N - 2 + TBX_SK + 31) / 32;
+    std::vector<uint32_t> tab;
+    tab.reserve((size_t)G * NBP);
+    for (int w = 0; w <= (NBP - 1) + 2 * (G - 1); ++w)      // w = b + 2g: both dependencies have w-1
+        for (int g = 0; g < G; ++g) {
+            const int b = w - 2 * g;
+            if (b >= 0 && b < NBP) tab.push_back(((uint32_t)g << 16) | (uint32_t)b);
+        }
+    uint32_t *d = nullptr;
+    CU(cudaMalloc(&d, tab.size() * sizeof(uint32_t)));
+    CU(cudaMemcpyAsync(d, tab.data(), tab.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    (*h->job_tables)[key] = d;
+    *out = d;
+    return EQ_OK;
+}
+
+static int lin_solve_exact_tb(eq_fluid *h, const LinSolveReq *req, int nreq, int64_t iters) {
+    const EqLayout L = h->L;
+    const int NBP = (L.N - 2 + TBX_SK + 31) / 32;
+    const int NC = (L.N + EQ_LSX_CW - 1) / EQ_LSX_CW;
+    int64_t done = 0;
+    while (done < iters) {
+        const int kc = (int)std::min<int64_t>(LSX_KMAX, iters - done);
+        const int G = (kc + TBX_T - 1) / TBX_T;
+        const uint32_t *jobs = nullptr;
+        TRY(get_tb_job_table(h, G, &jobs));
+        TbxParams p;
+        memset(&p, 0, sizeof(p));
+        p.nprob = nreq;
+        const size_t prog_words = (size_t)G * NBP;
+        for (int i = 0; i < nreq; ++i) {
+            p.prob[i].x = req[i].x;
+            p.prob[i].x0 = req[i].x0;
+            p.prob[i].raw = h->tb_raw[i];
+            p.prob[i].edge = h->tb_edge[i];
+            p.prob[i].progress = h->flags + 8 + (size_t)i * prog_words;
+            p.prob[i].a = req[i].a;
+            p.prob[i].c_recip = 1.0f / req[i].c;                       // fluid.rs:311
+            p.prob[i].orient = req[i].orient;
+        }
+        p.codes = h->codes;
+        p.chunk_flags = h->chunk_flags_tb;
+        p.row_fluid = h->row_fluid;
+        p.col_fluid = h->col_fluid;
+        p.jobs = jobs;
+        p.njobs = G * NBP;
+        p.N = L.N;
+        p.P = L.P;
+        p.K = kc;
+        p.G = G;
+        p.NBP = NBP;
+        p.NC = NC;
+        p.ticket = h->flags;
+        p.error = reinterpret_cast<int *>(h->flags + 1);
+        p.rotate_roles = env_int("EQ_LSX_ROT", 1);
+        p.debug_nodeps = getenv("EQ_LSX_NODEPS") ? 1 : 0;
+        p.passive_fast_frames = (h->all_cols_fluid && env_int("EQ_TB_FAST_FRAMES", 1)) ? 1 : 0;
+        CU(cudaMemsetAsync(h->flags, 0, sizeof(unsigned), h->stream));
+        CU(cudaMemsetAsync(h->flags + 8, 0, (size_t)nreq * prog_words * sizeof(unsigned), h->stream));
+        const int grid = std::min(h->tb_ctas, p.njobs * nreq);
+        EQ_LAUNCH(k_linsolve_tb, grid, LSX_THREADS, TBX_SMEM_BYTES, h->stream, p);
+        TRY(check_launch("k_linsolve_tb"));
         done += kc;
     }
     for (int i = 0; i < nreq; ++i) {
@@ -487,6 +584,8 @@ static int lin_solve(eq_fluid *h, const LinSolveReq *req, int nreq, int64_t iter
         return lin_solve_red_black(h, req, nreq, iters);
     }
     ProfScope ps(h, CAT_LS, (int)((iters + LSX_KMAX - 1) / LSX_KMAX) + nreq);
+    static const bool tb_off = getenv("EQ_LSX_TB") && atoi(getenv("EQ_LSX_TB")) == 0;
+    if (h->world == 1 && TBX_T > 1 && !tb_off) return lin_solve_exact_tb(h, req, nreq, iters);
     return lin_solve_exact(h, req, nreq, iters);
 }
 
@@ -640,6 +739,17 @@ static int alloc_handle(const EqParams *params, eq_fluid **out) {
     CU(cudaMalloc(&h->col_fluid, h->L.P));
     CU(cudaMalloc(&h->counts, 4 * sizeof(unsigned)));
     CU(cudaMalloc(&h->chunk_flags, 2 * (size_t)((h->L.N - 2 + 31) / 32) * ((h->L.N + EQ_LSX_CW - 1) / EQ_LSX_CW)));
+    {
+        const int NBP = (h->L.N - 2 + TBX_SK + 31) / 32;
+        CU(cudaMalloc(&h->chunk_flags_tb, 2 * (size_t)NBP * ((h->L.N + EQ_LSX_CW - 1) / EQ_LSX_CW)));
+        for (int i = 0; i < 2; ++i) {
+            const size_t nraw = (size_t)TBX_T * NBP * h->L.P, nedge = (size_t)std::max(1, TBX_T - 1) * NBP * 2 * h->L.P;
+            CU(cudaMalloc(&h->tb_raw[i], nraw * sizeof(float)));
+            CU(cudaMemsetAsync(h->tb_raw[i], 0, nraw * sizeof(float), h->stream));
+            CU(cudaMalloc(&h->tb_edge[i], nedge * sizeof(float)));
+            CU(cudaMemsetAsync(h->tb_edge[i], 0, nedge * sizeof(float), h->stream));
+        }
+    }
     const int NB = (h->L.N - 2 + 31) / 32;
     for (int i = 0; i < 2; ++i) {
         CU(cudaMalloc(&h->raw[i], (size_t)NB * h->L.P * sizeof(float)));
@@ -661,7 +771,14 @@ static int alloc_handle(const EqParams *params, eq_fluid **out) {
     int per_sm = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_linsolve_exact, LSX_THREADS, LSX_SMEM_BYTES));
     h->lsx_ctas = std::max(1, per_sm) * h->sm_count;
+    {
+        CU(cudaFuncSetAttribute(k_linsolve_tb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TBX_SMEM_BYTES));
+        int tb_per_sm = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tb_per_sm, k_linsolve_tb, LSX_THREADS, TBX_SMEM_BYTES));
+        h->tb_ctas = std::max(1, tb_per_sm) * h->sm_count;
+    }
     if (const char *e = getenv("EQ_LSX_CTAS_PER_SM")) h->lsx_ctas = std::max(1, std::min(per_sm, atoi(e))) * h->sm_count;
+    if (const char *e = getenv("EQ_LSX_CTAS_PER_SM")) h->tb_ctas = std::min(h->tb_ctas, std::max(1, atoi(e)) * h->sm_count);
     if (getenv("EQ_LSX_TRACE")) {
         CU(cudaMalloc(&h->lsx_trace, 4 * 8 * 128 * sizeof(unsigned long long)));
         CU(cudaMemsetAsync(h->lsx_trace, 0, 4 * 8 * 128 * sizeof(unsigned long long), h->stream));
@@ -738,6 +855,11 @@ int eq_destroy(eq_fluid *h) {
     cudaFree(h->col_fluid);
     cudaFree(h->counts);
     cudaFree(h->chunk_flags);
+    cudaFree(h->chunk_flags_tb);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(h->tb_raw[i]);
+        cudaFree(h->tb_edge[i]);
+    }
     cudaFree(h->lsx_stats);
     cudaFree(h->lsx_trace);
     cudaFree(h->lsx_jobtimes);

@@ -20,7 +20,10 @@
 #define EQ_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 #endif
 
-#define EQ_ROW_PAD 32
+#define EQ_ROW_PAD 48
+#ifndef TBX_T
+#define TBX_T 2      // iterations per job of the temporally blocked wavefront solver (k_linsolve_tb.cuh)
+#endif
 #ifndef EQ_LSX_CW
 #define EQ_LSX_CW 16   // chunk width (columns) of the wavefront solver: staging / write-back / flag granularity
 #endif
@@ -193,4 +196,19 @@ __device__ __forceinline__ float gs_update(float x0, float right, float left, fl
     s = __fadd_rn(s, down);
     s = __fadd_rn(s, up);
     return __fmul_rn(__fadd_rn(x0, __fmul_rn(a, s)), c_recip);
+}
+
+// Warp scheduler balance for the warp-specialised kernels.  A warp runs on sub-partition
+// (hardware warp slot % 4); a 4-warp CTA occupies slots 4s..4s+3, so "warp 0 computes" would put
+// the compute warps of ALL co-resident CTAs on sub-partition 0 while the other three idle along
+// with the loaders and storers.  Rotating the roles by the CTA's slot number spreads them.
+// Roles are still one warp each whatever the slots turn out to be: only balance depends on it.
+__device__ __forceinline__ unsigned eq_cta_slot_rotation() {
+#ifdef EQ_HOST_EMU
+    return blockIdx.x & 3u;
+#else
+    unsigned wid;
+    asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
+    return (wid >> 2) & 3u;
+#endif
 }

@@ -97,6 +97,7 @@ struct LsxParams {
     unsigned *ticket;
     int *error;
     int slack;                   // a consumer asks its producers to be this many chunks further ahead than strictly needed
+    int rotate_roles;            // 1: spread the roles over the warp schedulers (eq_cta_slot_rotation); EQ_LSX_ROT=0 turns it off
     int debug_nodeps;            // EQ_LSX_NODEPS=1: skip the dependency waits (WRONG results; throughput experiments only)
     unsigned long long *stats;   // optional [16] cycle counters (EQ_LSX_STATS=1), see eq_api.cu
     unsigned long long *jobtimes; // optional [2 * njobs * nprob] start/end ns of every job (EQ_LSX_JOBTIMES=1)
@@ -116,63 +117,59 @@ __device__ __forceinline__ unsigned long long lsx_gtime() { unsigned long long t
 #define LSX_TRACE(ev, q) do { if (p.trace && lane == 0 && k == p.K - 1 && (b < 3 || b == p.NB - 1) && (q) >= 200 && (q) < 328) p.trace[((size_t)(b < 3 ? b : 3) * 8 + (ev)) * 128 + (q) - 200] = lsx_gtime(); } while (0)
 #define LSX_STAT(slot, v) do { if (p.stats && lane == 0) atomicAdd(p.stats + (slot), (unsigned long long)(v)); } while (0)
 
-// ---- waiting primitives: lane 0 waits, the result is broadcast; every loop can be aborted ----
+// ---- waiting primitives: every loop can be aborted ----
+// ALL 32 lanes poll (the way the consumer warps of a TMA pipeline do).  A version where lane 0 polled
+// and broadcast the result left the warp split 1 + 31 in the kernel's main loops -- ncu showed every
+// step issued twice (16 threads per instruction on average) with each shuffle taking the
+// WARPSYNC.COLLECTIVE slow path.  Polling with the whole warp has no lane-dependent branch at all.
 // Dependency flags of other jobs (global memory, acquire).
 __device__ __forceinline__ bool lsx_wait_flags(const unsigned *f1, unsigned n1, bool sys1, const unsigned *f2, unsigned n2,
                                                bool sys2, int *error, int lane) {
-    int ok = 1;
-    if (lane == 0) {
-        unsigned spins = 0;
-        // spin with relaxed loads (an acquire load is followed by an L1 invalidate, CCTL.IVALL, which
-        // the five loaders of an SM would otherwise issue every few hundred cycles), then take one
-        // acquire load of the flag that was seen set: it reads from the release and synchronises.
-        // (a flag written by the neighbouring GPU is read at system scope)
-        while ((f1 && (sys1 ? ld_relaxed_sys_u32(f1) : ld_relaxed_u32(f1)) < n1) ||
-               (f2 && (sys2 ? ld_relaxed_sys_u32(f2) : ld_relaxed_u32(f2)) < n2)) {
-            __nanosleep(64);
-            if ((++spins & 1023u) == 0) {
-                if (spins >= LSX_SPIN_LIMIT) {
-                    *error = 1;
-                    ok = 0;
-                    break;
-                }
-                if (ld_volatile_s32(error) != 0) {
-                    ok = 0;
-                    break;
-                }
+    bool ok = true;
+    unsigned spins = 0;
+    // spin with relaxed loads (an acquire load is followed by an L1 invalidate, CCTL.IVALL, which
+    // the five loaders of an SM would otherwise issue every few hundred cycles), then take one
+    // acquire load of the flag that was seen set: it reads from the release and synchronises.
+    // (a flag written by the neighbouring GPU is read at system scope)
+    while ((f1 && (sys1 ? ld_relaxed_sys_u32(f1) : ld_relaxed_u32(f1)) < n1) ||
+           (f2 && (sys2 ? ld_relaxed_sys_u32(f2) : ld_relaxed_u32(f2)) < n2)) {
+        __nanosleep(64);
+        if ((++spins & 1023u) == 0) {
+            if (spins >= LSX_SPIN_LIMIT) {
+                if (lane == 0) *error = 1;
+                ok = false;
+                break;
+            }
+            if (ld_volatile_s32(error) != 0) {
+                ok = false;
+                break;
             }
         }
-        if (ok) {
-            if (f1) (void)(sys1 ? ld_acquire_sys_u32(f1) : ld_acquire_u32(f1));
-            if (f2) (void)(sys2 ? ld_acquire_sys_u32(f2) : ld_acquire_u32(f2));
-        }
     }
-    ok = __shfl_sync(0xffffffffu, ok, 0);
-    __syncwarp();
-    return ok != 0;
+    if (ok) {
+        if (f1) (void)(sys1 ? ld_acquire_sys_u32(f1) : ld_acquire_u32(f1));
+        if (f2) (void)(sys2 ? ld_acquire_sys_u32(f2) : ld_acquire_u32(f2));
+    }
+    return __all_sync(0xffffffffu, ok) != 0;
 }
 // An mbarrier of this CTA.
 __device__ __forceinline__ bool lsx_wait_bar(uint32_t bar, uint32_t parity, int *error, int lane) {
-    int ok = 1;
-    if (lane == 0) {
-        unsigned spins = 0;
-        while (!mbar_try_wait(bar, parity)) {
-            if ((++spins & 255u) == 0) {
-                if (spins >= LSX_SPIN_LIMIT) {
-                    *error = 2;
-                    ok = 0;
-                    break;
-                }
-                if (ld_volatile_s32(error) != 0) {
-                    ok = 0;
-                    break;
-                }
+    bool ok = true;
+    unsigned spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++spins & 255u) == 0) {
+            if (spins >= LSX_SPIN_LIMIT) {
+                if (lane == 0) *error = 2;
+                ok = false;
+                break;
+            }
+            if (ld_volatile_s32(error) != 0) {
+                ok = false;
+                break;
             }
         }
     }
-    ok = __shfl_sync(0xffffffffu, ok, 0);
-    __syncwarp();
-    return ok != 0;
+    return __all_sync(0xffffffffu, ok) != 0;
 }
 
 // Everything the three roles of a job share.
@@ -526,7 +523,12 @@ __global__ void __launch_bounds__(LSX_THREADS) k_linsolve_exact(const LsxParams 
     const int total = p.njobs * p.nprob;
     // broadcast the warp index so the compiler knows the role branches below are warp-uniform
     // (otherwise every __shfl/__syncwarp in the roles becomes an out-of-line WARPSYNC.COLLECTIVE)
-    const int warp = __shfl_sync(0xffffffffu, (int)threadIdx.x >> 5, 0), lane = (int)threadIdx.x & 31;
+    const int lane = (int)threadIdx.x & 31;
+    if (threadIdx.x == 0) sts_u32(sbase + LSX_MISC_OFF + 8u, p.rotate_roles ? eq_cta_slot_rotation() : 0u);
+    __syncthreads();
+    // role 0 compute, 1 loader, 2 storer, 3 publisher (uniform per warp: taken through a shuffle so that
+    // the compiler keeps the dispatch branch-uniform)
+    const int warp = __shfl_sync(0xffffffffu, (((int)threadIdx.x >> 5) - (int)lds_u32(sbase + LSX_MISC_OFF + 8u)) & 3, 0);
     for (;;) {
         __syncthreads();                               // the previous job is finished in all three roles
         if (threadIdx.x == 0) {

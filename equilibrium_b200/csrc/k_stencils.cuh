@@ -27,7 +27,8 @@ __device__ __forceinline__ unsigned eq_cell_code(const uint8_t *cells, int i, in
 
 // pass 0: codes + row/column "has fluid" flags + counts; pass 1: fill the lists
 __global__ void k_build_codes(const uint8_t *__restrict__ cells, uint8_t *__restrict__ codes,
-                              uint8_t *row_fluid, uint8_t *col_fluid, uint8_t *chunk_flags, unsigned *counts,
+                              uint8_t *row_fluid, uint8_t *col_fluid, uint8_t *chunk_flags, uint8_t *chunk_flags_tb,
+                              unsigned *counts,
                               uint2 *row_list, uint2 *col_list, int pass, EqLayout L) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y;
@@ -42,6 +43,15 @@ __global__ void k_build_codes(const uint8_t *__restrict__ cells, uint8_t *__rest
         }
         // (band, chunk) summaries for the wavefront solver: band = 32 rows from row 1, chunk = EQ_LSX_CW columns
         const int NB = (L.N - 2 + 31) / 32, NC = (L.N + EQ_LSX_CW - 1) / EQ_LSX_CW;
+        // the temporally blocked solver uses bands that move up 2 rows per iteration: band b reads the
+        // codes of rows 32b-SK .. 32b+32 (SK = 2(T-1)), so a code in row j concerns bands (j-1)/32 .. (j+SK)/32
+        const int SK = 2 * (TBX_T - 1), NBP = (L.N - 2 + SK + 31) / 32;
+        if (code & 15u) {
+            for (int bb = (j - 1) / 32; bb <= min((j + SK) / 32, NBP - 1); ++bb) {
+                if (code & 3u) chunk_flags_tb[(size_t)bb * NC + i / EQ_LSX_CW] = 1;
+                if (code & 12u) chunk_flags_tb[(size_t)NBP * NC + (size_t)bb * NC + i / EQ_LSX_CW] = 1;
+            }
+        }
         const bool owned = (j >= L.row0 && j < L.row1);   // the sparse lists drive stand-alone boundary passes
         if (code & 3u) {
             if (owned) atomicAdd(&counts[0], 1u);

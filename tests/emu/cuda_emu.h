@@ -127,6 +127,17 @@ static inline T __shfl_sync(unsigned, T v, int src) {
     return eq_emu_exchange(v, src);
 }
 
+// full warps only (the wavefront kernels): AND of the predicate over the 32 lanes
+static inline int __all_sync(unsigned, int pred) {
+    eq_emu::WarpState *w = eq_emu::ctx.warp;
+    w->xch[eq_emu::ctx.lane] = pred ? 1u : 0u;
+    w->bar.arrive_and_wait();
+    int all = 1;
+    for (int l = 0; l < 32; ++l) all &= (int)w->xch[l];
+    w->bar.arrive_and_wait();
+    return all;
+}
+
 // ---- memory model stand-ins --------------------------------------------------
 static inline void __threadfence_system() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }

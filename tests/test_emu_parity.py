@@ -23,6 +23,22 @@ def test_lin_solve_exact(oracle, emu_lib, orient, n, k, rects):
 
 
 @pytest.mark.parametrize("orient", [P.ROW, P.COL, P.PASSIVE])
+@pytest.mark.parametrize("n,k", [(97, 3), (98, 4), (99, 5), (100, 1), (130, 3), (131, 2)])
+def test_lin_solve_exact_last_band_under_skew(oracle, emu_lib, orient, n, k):
+    # Temporal blocking moves a band up two rows per fused iteration, so the row N-2 (and the
+    # frame row behind it) is owned by different bands at different sub-steps around N = 32m+2;
+    # odd K leaves a shorter last group.
+    P.check_lin_solve(oracle, emu_lib, n, k, [(n - 12, 3, n - 1, 9), (5, n - 6, 40, n - 1), (30, 30, 36, 66)], orient)
+
+
+@pytest.mark.parametrize("n,k", [(98, 4), (131, 3)])
+def test_lin_solve_passive_with_a_walled_off_column(oracle, emu_lib, n, k):
+    # An obstacle spanning the full height leaves columns without a NoWall cell: their frame-row
+    # cells must keep their values (quirk Q6), so the Passive frame bands fall back to the general loop.
+    P.check_lin_solve(oracle, emu_lib, n, k, [(40, 1, 43, n - 1), (5, n - 6, 30, n - 1)], P.PASSIVE)
+
+
+@pytest.mark.parametrize("orient", [P.ROW, P.COL, P.PASSIVE])
 def test_lin_solve_exact_fast_and_general_macro_steps(oracle, emu_lib, orient):
     # N >= 97 is needed for a macro step with every lane on interior columns; with one small
     # rectangle most (band, chunk) pairs are code-free and take the branch-free fast loop,
