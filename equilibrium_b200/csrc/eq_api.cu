@@ -432,6 +432,7 @@ static int lin_solve_exact(eq_fluid *h, const LinSolveReq *req, int nreq, int64_
         p.stats = h->lsx_stats;
         p.debug_nodeps = getenv("EQ_LSX_NODEPS") ? 1 : 0;
         p.rotate_roles = env_int("EQ_LSX_ROT", 1);
+        p.pub_batch = std::max(1, env_int("EQ_LSX_PUBBATCH", L.N >= 8192 ? 8 : 4));
         p.slack = getenv("EQ_LSX_SLACK") ? atoi(getenv("EQ_LSX_SLACK")) : 0;
         p.trace = h->lsx_trace;
         p.jobtimes = nullptr;
@@ -531,8 +532,28 @@ static int lin_solve_exact_tb(eq_fluid *h, const LinSolveReq *req, int nreq, int
         p.ticket = h->flags;
         p.error = reinterpret_cast<int *>(h->flags + 1);
         p.rotate_roles = env_int("EQ_LSX_ROT", 1);
+        p.pub_batch = std::max(1, env_int("EQ_LSX_PUBBATCH", L.N >= 8192 ? 4 : 2));
         p.debug_nodeps = getenv("EQ_LSX_NODEPS") ? 1 : 0;
         p.passive_fast_frames = (h->all_cols_fluid && env_int("EQ_TB_FAST_FRAMES", 1)) ? 1 : 0;
+        p.trace = h->lsx_trace;
+        p.trace_g = G - 1;
+        p.trace_b = 200;
+        p.trace_q = 200;
+        if (const char *e = getenv("EQ_LSX_TRACE")) {
+            int tg = 0, tb = 0, tq = 200;
+            if (sscanf(e, "%d,%d,%d", &tg, &tb, &tq) >= 2) { p.trace_g = std::min(tg, G - 1); p.trace_b = tb; p.trace_q = tq; }
+        }
+        p.jobtimes = nullptr;
+        if (getenv("EQ_LSX_JOBTIMES")) {
+            const size_t n = 4 * (size_t)G * NBP;
+            if (h->lsx_jobtimes_n < n) {
+                cudaFree(h->lsx_jobtimes);
+                CU(cudaMalloc(&h->lsx_jobtimes, n * sizeof(unsigned long long)));
+                h->lsx_jobtimes_n = n;
+            }
+            CU(cudaMemsetAsync(h->lsx_jobtimes, 0, n * sizeof(unsigned long long), h->stream));
+            p.jobtimes = h->lsx_jobtimes;
+        }
         CU(cudaMemsetAsync(h->flags, 0, sizeof(unsigned), h->stream));
         CU(cudaMemsetAsync(h->flags + 8, 0, (size_t)nreq * prog_words * sizeof(unsigned), h->stream));
         const int grid = std::min(h->tb_ctas, p.njobs * nreq);

@@ -97,6 +97,8 @@ struct LsxParams {
     unsigned *ticket;
     int *error;
     int slack;                   // a consumer asks its producers to be this many chunks further ahead than strictly needed
+    int pub_batch;               // the publisher releases progress every pub_batch chunks (and at the end): one release
+                                 // costs ~4 us of fence whatever it covers; one chunk per release paces the whole chain
     int rotate_roles;            // 1: spread the roles over the warp schedulers (eq_cta_slot_rotation); EQ_LSX_ROT=0 turns it off
     int debug_nodeps;            // EQ_LSX_NODEPS=1: skip the dependency waits (WRONG results; throughput experiments only)
     unsigned long long *stats;   // optional [16] cycle counters (EQ_LSX_STATS=1), see eq_api.cu
@@ -367,7 +369,7 @@ struct LsxJob {
             if (lane == 0) {
                 unsigned spins = 0;
                 int have;
-                while ((have = (int)lds_acquire_cta_u32(cnt)) <= q) {     // chunks whose stores are issued
+                while ((have = (int)lds_acquire_cta_u32(cnt)) < min(q + p.pub_batch, NC)) {     // chunks whose stores are issued
                     __nanosleep(64);
                     if ((++spins & 1023u) == 0) {
                         if (spins >= LSX_SPIN_LIMIT) { *p.error = 3; ok = 0; break; }

@@ -22,6 +22,7 @@
 // Single GPU only (the row-slab path keeps using k_linsolve_exact).
 #pragma once
 #include "k_linsolve_exact.cuh"
+#include <type_traits>
 
 #ifndef TBX_T
 #define TBX_T 2                                   // iterations per job
@@ -62,10 +63,17 @@ struct TbxParams {
     int N, P, K, G, NBP, NC;     // K iterations in G groups of TBX_T (the last one may be shorter)
     unsigned *ticket;
     int *error;
+    int pub_batch;               // the publisher releases progress every pub_batch chunks (and at the end): one release
+                                 // costs ~4 us of fence whatever it covers; one chunk per release paces the whole chain
     int rotate_roles;            // see LsxParams
     int debug_nodeps;            // EQ_LSX_NODEPS=1: skip the dependency waits (WRONG results; throughput experiments only)
     int passive_fast_frames;     // every interior column has a NoWall cell: Passive frame-row copies are unconditional
+    int trace_g, trace_b, trace_q;  // EQ_LSX_TRACE=g,b,q: group, first band and first chunk traced
+    unsigned long long *trace;    // optional event trace (EQ_LSX_TRACE=1): [4 bands][8 events][128 chunks] ns, see dump_lsx_stats
+    unsigned long long *jobtimes; // optional [4 * njobs] (problem 0): start, first chunk ready, end (ns), SM id (EQ_LSX_JOBTIMES=file)
 };
+
+#define TBX_TRACE(ev, q) do { if (p.trace && lane == 0 && g == p.trace_g && b >= p.trace_b && b < p.trace_b + 4 && (q) >= p.trace_q && (q) < p.trace_q + 128) p.trace[((size_t)(b - p.trace_b) * 8 + (ev)) * 128 + (q) - p.trace_q] = lsx_gtime(); } while (0)
 
 template <int ORIENT>
 struct TbxJob {
@@ -129,6 +137,7 @@ struct TbxJob {
         for (int q = 0; q < NC; ++q) {
             if (q + LSX_PF < NC) prefetch_l2(x0 + (size_t)(j0 + lane) * P + LSX_CW * (q + LSX_PF));
             if (q >= LSX_SLOTS && !lsx_wait_bar(bar_free(q), use_parity(q - LSX_SLOTS), p.error, lane)) return false;
+            TBX_TRACE(0, q);
             if (!lsx_wait_flags(flag_prev, (unsigned)q + 1u, false, flag_above, (unsigned)q + 1u, false, p.error, lane)) return false;
             const uint32_t slot = (uint32_t)(q % LSX_SLOTS) * (LSX_CW * 4u);
             const int col0 = LSX_CW * q;
@@ -182,6 +191,7 @@ struct TbxJob {
                 }
             }
             cp_async_mbar_arrive_noinc(bar_full(q));
+            TBX_TRACE(1, q);
         }
         return true;
     }
@@ -195,6 +205,7 @@ struct TbxJob {
         const bool has_below = (b + 1 < NBP);
         for (int q = 0; q < NC; ++q) {
             if (!lsx_wait_bar(bar_done(q), use_parity(q), p.error, lane)) return false;
+            TBX_TRACE(4, q);
             const uint32_t slot = (uint32_t)(q % LSX_SLOTS) * (LSX_CW * 4u);
             const int col0 = LSX_CW * q;
             // rows of the last sub-step (iteration k0+nsub-1); Passive also keeps the frame rows it touched
@@ -226,6 +237,7 @@ struct TbxJob {
                 }
             }
             __syncwarp();
+            TBX_TRACE(5, q);
             if (lane == 0) {
                 mbar_arrive(bar_free(q));
                 sts_release_cta_u32(sbase + TBX_MISC_OFF + 4u, (uint32_t)q + 1u);
@@ -243,7 +255,7 @@ struct TbxJob {
             if (lane == 0) {
                 unsigned spins = 0;
                 int have;
-                while ((have = (int)lds_acquire_cta_u32(cnt)) <= q) {
+                while ((have = (int)lds_acquire_cta_u32(cnt)) < min(q + p.pub_batch, NC)) {
                     __nanosleep(64);
                     if ((++spins & 1023u) == 0) {
                         if (spins >= LSX_SPIN_LIMIT) { *p.error = 3; ok = 0; break; }
@@ -252,7 +264,9 @@ struct TbxJob {
                 }
                 if (ok) {
                     q = have;
+                    TBX_TRACE(6, q - 1);
                     st_release_u32(my_flag, (unsigned)q);
+                    TBX_TRACE(7, q - 1);
                 }
             }
             q = __shfl_sync(0xffffffffu, q, 0);
@@ -270,7 +284,7 @@ struct TbxJob {
         // per sub-step: my row, its shared addresses, where the value above the first row comes from
         int row[TBX_T];
         bool in_row[TBX_T], first[TBX_T], rowfl[TBX_T], frame_from_edge[TBX_T], frame_top[TBX_T], frame_bot[TBX_T];
-        uint32_t xs_row[TBX_T], x0_row[TBX_T], cs_row[TBX_T], top_base[TBX_T];
+        uint32_t xs_row[TBX_T], x0_row[TBX_T], cs_row[TBX_T], top_base[TBX_T], down_row[TBX_T];
         float cur[TBX_T], prev2[TBX_T], prev_up[TBX_T];
 #pragma unroll
         for (int t = 0; t < TBX_T; ++t) {
@@ -284,6 +298,8 @@ struct TbxJob {
             const int tr = trow(row[t]);                          // may be out of the tile for inactive lanes of band 0
             const int trc = min(max(tr, 0), TBX_XROWS - 2);
             xs_row[t] = xs0 + (uint32_t)trc * 512u;
+            // fast loops: where the lower neighbour is read (see frame_from_edge in the general loop)
+            down_row[t] = frame_from_edge[t] ? xs_row[t] : xs_row[t] + 512u;
             x0_row[t] = sbase + TBX_X0_OFF + (uint32_t)min(max(tr - 1, 0), TBX_X0ROWS - 1) * 512u;
             cs_row[t] = cs0 + (uint32_t)trc * 128u;
             top_base[t] = (b == 0) ? xs0 + (uint32_t)trow(0) * 512u : sbase + TBX_RAWIN_OFF + (uint32_t)t * 512u;
@@ -291,14 +307,174 @@ struct TbxJob {
         }
         const uint32_t raw_out = sbase + TBX_RAWOUT_OFF;
 
+        int m_cur = 0;
+        const uint32_t last_col = ((uint32_t)(N - 1) & 127u) << 2;
+        // ---- fast loop: straight-line code for the 16 steps x T sub-steps of a macro step in which nothing needs
+        // a per-cell code lookup.  The operands of step s+1 are fetched before the arithmetic of step s (nobody
+        // writes them later than step s-1), so the step-to-step chain of a sub-step is SHFL -> 3 FADD, FMUL, FADD,
+        // FMUL, and the T chains interleave.
+        //   ZONE 0: every lane of every sub-step is on an interior column (MODE_FAST).
+        //   ZONE 1 / 2: the macro steps at the start / end of the rows (MODE_EDGE), where lanes are still left of
+        //   column 1 or already right of column N-2: the same loop plus range predicates (compares against
+        //   immediates once unrolled), the frame-column pass-through, AdjustRow's codes (columns 1 and N-2 always
+        //   carry one) and Passive's frame-column copies.  These steps open and close every job: the band below
+        //   cannot start before the first ones are done nor finish before the last, so their duration is the lag
+        //   between consecutive bands and the solve is a chain of NB such lags -- they must not be slow.
+        const bool lean_edges = (ORIENT == EQ_ADJUST_ROW) || (ORIENT == EQ_PASSIVE && (!owns_frame_row() || p.passive_fast_frames));
+        auto fast_steps = [&](auto zone_c) {
+            constexpr int ZONE = decltype(zone_c)::value;
+            const int cb = LSX_CW * m_cur - lane;                 // column of sub-step 0 at the first step
+            const uint32_t ob = ((uint32_t)cb & 127u) << 2;
+            float right[TBX_T], down[TBX_T], x0v[TBX_T], topv[TBX_T];
+#pragma unroll
+            for (int t = 0; t < TBX_T; ++t) {
+                const uint32_t o = (ob - 4u * TBX_LAG * t) & 508u;
+                right[t] = lds_f32(xs_row[t] + ((o + 4u) & 508u));
+                down[t] = lds_f32(down_row[t] + o);
+                x0v[t] = lds_f32(x0_row[t] + o);
+                topv[t] = first[t] ? lds_f32(top_base[t] + o) : 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < LSX_CW; ++i) {
+#pragma unroll
+                for (int t = 0; t < TBX_T; ++t) {
+                    const int c = cb + i - TBX_LAG * t;
+                    const uint32_t o = (ob + 4u * i - 4u * TBX_LAG * t) & 508u;
+                    const uint32_t o1 = (o + 4u) & 508u, o2 = (o + 8u) & 508u, om1 = (o - 4u) & 508u;
+                    float up = __shfl_up_sync(0xffffffffu, cur[t], 1);
+                    if (first[t]) up = topv[t];
+                    const float right_n = lds_f32(xs_row[t] + o2);
+                    const float down_n = lds_f32(down_row[t] + o1);
+                    const float x0_n = lds_f32(x0_row[t] + o1);
+                    if (first[t]) topv[t] = lds_f32(top_base[t] + o1);
+                    float newv = gs_update(x0v[t], right[t], cur[t], down[t], up, a, c_recip);
+                    bool interior = in_row[t], fin = in_row[t];
+                    float F = cur[t];
+                    if (ZONE != 0) {
+                        const float self = lds_f32(xs_row[t] + o);
+                        const bool frame_col = in_row[t] & (ZONE == 1 ? (c == 0) : (c == N - 1));
+                        interior = in_row[t] & (ZONE == 1 ? (c >= 1) : (c <= N - 2));
+                        fin = in_row[t] & (ZONE == 1 ? (c >= 2) : (c <= N - 1));        // cf = c-1 in 1 .. N-2
+                        newv = interior ? newv : (frame_col ? self : cur[t]);
+                        if (ORIENT == EQ_ADJUST_ROW) {
+                            const unsigned code = lds_u8(cs_row[t] + (om1 >> 2)) & 3u;
+                            F = (code == EQ_CODE_ROW_RIGHT) ? -newv : ((code == EQ_CODE_ROW_LEFT) ? -prev2[t] : cur[t]);
+                        }
+                    }
+                    if (fin) sts_f32(xs_row[t] + om1, F);
+                    if (ORIENT == EQ_PASSIVE) {
+                        // fluid.rs:182-186 (every col_fluid is set here: passive_fast_frames)
+                        if (ZONE == 1) { if (fin & rowfl[t] & (c == 2)) sts_f32(xs_row[t], cur[t]); }
+                        if (ZONE == 2) { if (fin & rowfl[t] & (c == N - 1)) sts_f32(xs_row[t] + last_col, cur[t]); }
+                        if (fin & frame_top[t]) sts_f32(xs_row[t] - 512u + om1, cur[t]);
+                        if (fin & frame_bot[t]) sts_f32(xs_row[t] + 512u + om1, cur[t]);
+                    }
+                    if (interior & (lane == 31)) sts_f32(raw_out + (uint32_t)t * 512u + o, newv);
+                    prev2[t] = cur[t];
+                    prev_up[t] = up;
+                    cur[t] = newv;
+                    right[t] = right_n;
+                    down[t] = down_n;
+                    x0v[t] = x0_n;
+                    __syncwarp();
+                }
+            }
+        };
+
+        // ---- general loop: macro steps that touch fix-up codes (MODE_CODED) or run off the ends of the rows
+        // (MODE_EDGE, RANGED).  Flat on purpose -- selects and single-level predicated stores: every shared
+        // address is valid for any column (the ring wraps), so operands are loaded unconditionally and the
+        // tests only pick results.  (A version with nested ifs compiled to divergent branches and took ~10 us
+        // per macro step against 1.1 us for the fast loop.  The EDGE steps open and close every job: the band
+        // below cannot start before the first ones are done nor finish before the last, so their duration is
+        // the lag between consecutive bands and the solve is a chain of NB such lags.)
+        auto general_steps = [&](auto ranged_c) {
+            constexpr bool RANGED = decltype(ranged_c)::value;
+            const int s_end = min(LSX_CW * m_cur + LSX_CW, S);
+            for (int s = LSX_CW * m_cur; s < s_end; ++s) {
+#pragma unroll
+                for (int t = 0; t < TBX_T; ++t) {
+                    if (t < nsub) {
+                        const int c = s - lane - TBX_LAG * t;       // column this lane computes now (0 = left frame cell)
+                        const int cf = c - 1;                        // column finalised now
+                        const uint32_t o = ((uint32_t)c & 127u) << 2;
+                        const uint32_t om1 = (o - 4u) & 508u;
+                        const float up = __shfl_up_sync(0xffffffffu, cur[t], 1);
+                        const float right = lds_f32(xs_row[t] + ((o + 4u) & 508u));
+                        float down = lds_f32(xs_row[t] + 512u + o);
+                        const float x0v = lds_f32(x0_row[t] + o);
+                        const float self = lds_f32(xs_row[t] + o);
+                        const float top = first[t] ? lds_f32(top_base[t] + o) : up;
+                        if (ORIENT == EQ_PASSIVE) {
+                            // Row N-2 arrived as band b-1's LAST row of the previous sub-step: that band copied it into
+                            // the frame row N-1 of ITS tile (where col_fluid), mine still holds the older frame.
+                            const bool colf_c = lds_u8(cs0 + (o >> 2)) != 0;
+                            down = (frame_from_edge[t] & colf_c) ? self : down;
+                        }
+                        const bool gs_ok = in_row[t] & (!RANGED | ((c >= 1) & (c <= N - 2)));
+                        const bool pass_row = in_row[t] | ((ORIENT == EQ_ADJUST_COLUMN) & (row[t] == N - 1));
+                        const bool pass_ok = pass_row & (!RANGED | ((c >= 0) & (c <= N - 1)));
+                        const float gval = gs_update(x0v, right, cur[t], down, top, a, c_recip);
+                        const float newv = gs_ok ? gval : (pass_ok ? self : cur[t]);
+                        const bool fin = in_row[t] & (!RANGED | ((cf >= 1) & (cf <= N - 2)));
+                        float F = cur[t];
+                        if (ORIENT == EQ_ADJUST_ROW) {
+                            const unsigned code = lds_u8(cs_row[t] + (om1 >> 2)) & 3u;
+                            F = (code == EQ_CODE_ROW_RIGHT) ? -newv : ((code == EQ_CODE_ROW_LEFT) ? -prev2[t] : cur[t]);
+                        } else if (ORIENT == EQ_ADJUST_COLUMN) {
+                            const float dn = __shfl_down_sync(0xffffffffu, newv, 1);
+                            const unsigned code = lds_u8(cs_row[t] + (om1 >> 2)) & 12u;
+                            // lane 31's lower neighbour is either the frame row N-1 (in the tile) or the first
+                            // row of band b+1 at this sub-step, which patches the cell itself (below)
+                            const bool below_is_frame = (row[t] == N - 2);
+                            const float below = (lane < 31) ? dn : lds_f32(xs_row[t] + 512u + om1);
+                            const bool take_down = (code == EQ_CODE_COL_DOWN) & ((lane < 31) | below_is_frame);
+                            F = (code == EQ_CODE_COL_UP) ? -prev_up[t] : (take_down ? -below : cur[t]);
+                            // cell (c, j-1) above my first row belongs to band b-1 at this sub-step: it takes -R(c, j)
+                            // when its code says DOWN.  For an intermediate iteration the cell lives on in MY tile
+                            // (it is one of my edge rows); for the last one it is already in global x.
+                            const unsigned code0 = lds_u8(cs_row[t] - 128u + (o >> 2)) & 12u;
+                            const bool patch = gs_ok & (lane == 0) & (b > 0) & (code0 == EQ_CODE_COL_DOWN);
+                            if (patch & (t == nsub - 1)) x[(size_t)(row[t] - 1) * P + c] = -newv;
+                            if (patch & (t != nsub - 1)) sts_f32(xs_row[t] - 512u + o, -newv);
+                        }
+                        if (fin) sts_f32(xs_row[t] + om1, F);
+                        if (ORIENT == EQ_PASSIVE) {
+                            // fluid.rs:182-186, conditional per quirk Q6 (col_fluid is staged in row 0 of the code tile)
+                            if (RANGED) {
+                                if (fin & rowfl[t] & (cf == 1)) sts_f32(xs_row[t], cur[t]);
+                                if (fin & rowfl[t] & (cf == N - 2)) sts_f32(xs_row[t] + last_col, cur[t]);
+                            }
+                            const bool colf = lds_u8(cs0 + (om1 >> 2)) != 0;
+                            if (fin & colf & (row[t] == 1)) sts_f32(xs_row[t] - 512u + om1, cur[t]);
+                            if (fin & colf & (row[t] == N - 2)) sts_f32(xs_row[t] + 512u + om1, cur[t]);
+                        }
+                        if (gs_ok & (lane == 31)) sts_f32(raw_out + (uint32_t)t * 512u + o, newv);
+                        prev2[t] = cur[t];
+                        prev_up[t] = top;
+                        cur[t] = newv;
+                        __syncwarp();
+                    }
+                }
+            }
+        };
+
         if (!lsx_wait_bar(bar_full(0), 0u, p.error, lane)) return false;
+        if (p.jobtimes && lane == 0 && &pr == &p.prob[0]) p.jobtimes[4 * ((size_t)g * NBP + b) + 1] = lsx_gtime();
         for (int m = 0; m < M; ++m) {
             if (m + 1 < NC && !lsx_wait_bar(bar_full(m + 1), use_parity(m + 1), p.error, lane)) return false;
+            TBX_TRACE(2, m);
             const int mode = macro_mode(m);
-            const bool ranged = (mode == MODE_EDGE);
+            m_cur = m;
             const int s_end = min(LSX_CW * m + LSX_CW, S);
-            if (mode == MODE_FAST) {
-                // every lane of every sub-step is on an interior column and nothing needs a fix-up
+            if (nsub == TBX_T && mode == MODE_FAST) {
+                fast_steps(std::integral_constant<int, 0>{});
+            } else if (nsub == TBX_T && mode == MODE_EDGE && lean_edges && LSX_CW * m + LSX_CW - 1 <= N - 2) {
+                fast_steps(std::integral_constant<int, 1>{});       // start of the rows only
+            } else if (nsub == TBX_T && mode == MODE_EDGE && lean_edges && LSX_CW * m - 31 - TBX_LAG * (TBX_T - 1) >= 2) {
+                fast_steps(std::integral_constant<int, 2>{});       // end of the rows only
+            } else if (mode == MODE_FAST) {
+                // short last group (K not a multiple of TBX_T): same thing with the sub-step count tested
                 for (int s = LSX_CW * m; s < s_end; ++s) {
 #pragma unroll
                     for (int t = 0; t < TBX_T; ++t) {
@@ -307,14 +483,12 @@ struct TbxJob {
                             const uint32_t o1 = (o + 4u) & 508u, om1 = (o - 4u) & 508u;
                             float up = __shfl_up_sync(0xffffffffu, cur[t], 1);
                             const float right = lds_f32(xs_row[t] + o1);
-                            float down = lds_f32(xs_row[t] + 512u + o);
+                            const float down = lds_f32(down_row[t] + o);
                             const float x0v = lds_f32(x0_row[t] + o);
                             if (first[t]) up = lds_f32(top_base[t] + o);
-                            if (ORIENT == EQ_PASSIVE && frame_from_edge[t]) down = lds_f32(xs_row[t] + o);   // see the general loop
                             const float newv = gs_update(x0v, right, cur[t], down, up, a, c_recip);
                             if (in_row[t]) sts_f32(xs_row[t] + om1, cur[t]);
                             if (ORIENT == EQ_PASSIVE) {
-                                // fluid.rs:182-183 with every col_fluid set (passive_fast_frames)
                                 if (frame_top[t]) sts_f32(xs_row[t] - 512u + om1, cur[t]);
                                 if (frame_bot[t]) sts_f32(xs_row[t] + 512u + om1, cur[t]);
                             }
@@ -326,74 +500,12 @@ struct TbxJob {
                         }
                     }
                 }
+            } else if (mode == MODE_EDGE) {
+                general_steps(std::true_type{});
             } else {
-                for (int s = LSX_CW * m; s < s_end; ++s) {
-#pragma unroll
-                    for (int t = 0; t < TBX_T; ++t) {
-                        if (t < nsub) {
-                            const int c = s - lane - TBX_LAG * t;
-                            const int cf = c - 1;
-                            const uint32_t o = ((uint32_t)c & 127u) << 2;
-                            const uint32_t om1 = (o - 4u) & 508u;
-                            const float up = __shfl_up_sync(0xffffffffu, cur[t], 1);
-                            const float right = lds_f32(xs_row[t] + ((o + 4u) & 508u));
-                            float down = lds_f32(xs_row[t] + 512u + o);
-                            const float x0v = lds_f32(x0_row[t] + o);
-                            const float self = lds_f32(xs_row[t] + o);
-                            // Row N-2 arrived as band b-1's LAST row of the previous sub-step: that band copied it into
-                            // the frame row N-1 of ITS tile (Passive, where col_fluid), mine still holds the older frame.
-                            if (ORIENT == EQ_PASSIVE && frame_from_edge[t] && lds_u8(cs0 + (o >> 2))) down = self;
-                            const float top = first[t] ? lds_f32(top_base[t] + o) : up;
-                            const bool gs_ok = in_row[t] && (!ranged || (c >= 1 && c <= N - 2));
-                            const bool pass_ok = (!ranged || (c >= 0 && c <= N - 1)) && (in_row[t] || (ORIENT == EQ_ADJUST_COLUMN && row[t] == N - 1));
-                            const float gval = gs_update(x0v, right, cur[t], down, top, a, c_recip);
-                            const float newv = gs_ok ? gval : (pass_ok ? self : cur[t]);
-                            const bool fin = in_row[t] && (!ranged || (cf >= 1 && cf <= N - 2));
-                            float F = cur[t];
-                            if (ORIENT == EQ_ADJUST_ROW) {
-                                const unsigned code = lds_u8(cs_row[t] + (om1 >> 2)) & 3u;
-                                F = (code == EQ_CODE_ROW_RIGHT) ? -newv : ((code == EQ_CODE_ROW_LEFT) ? -prev2[t] : cur[t]);
-                            } else if (ORIENT == EQ_ADJUST_COLUMN) {
-                                const float dn = __shfl_down_sync(0xffffffffu, newv, 1);
-                                const unsigned code = lds_u8(cs_row[t] + (om1 >> 2)) & 12u;
-                                // lane 31's lower neighbour is either the frame row N-1 (in the tile) or the first
-                                // row of band b+1 at this sub-step, which patches the cell itself (below)
-                                const bool below_is_frame = (row[t] == N - 2);
-                                const float below = (lane < 31) ? dn : lds_f32(xs_row[t] + 512u + om1);
-                                const bool take_down = (code == EQ_CODE_COL_DOWN) && (lane < 31 || below_is_frame);
-                                F = (code == EQ_CODE_COL_UP) ? -prev_up[t] : (take_down ? -below : cur[t]);
-                                if (gs_ok && lane == 0 && b > 0) {
-                                    // cell (c, j-1) above my first row belongs to band b-1 at this sub-step: it takes
-                                    // -R(c, j) when its code says DOWN.  For an intermediate iteration the cell lives on
-                                    // in MY tile (it is one of my edge rows); for the last one it is already in global x.
-                                    const unsigned code0 = lds_u8(cs_row[t] - 128u + (o >> 2)) & 12u;
-                                    if (code0 == EQ_CODE_COL_DOWN) {
-                                        if (t == nsub - 1) x[(size_t)(row[t] - 1) * P + c] = -newv;
-                                        else sts_f32(xs_row[t] - 512u + o, -newv);
-                                    }
-                                }
-                            }
-                            if (fin) sts_f32(xs_row[t] + om1, F);
-                            if (ORIENT == EQ_PASSIVE && fin) {
-                                // fluid.rs:182-186, conditional per quirk Q6 (col_fluid is staged in row 0 of the code tile)
-                                if (ranged && rowfl[t]) {
-                                    if (cf == 1) sts_f32(xs_row[t], cur[t]);
-                                    if (cf == N - 2) sts_f32(xs_row[t] + (((uint32_t)(N - 1) & 127u) << 2), cur[t]);
-                                }
-                                if ((row[t] == 1 || row[t] == N - 2) && lds_u8(cs0 + (om1 >> 2))) {
-                                    if (row[t] == 1) sts_f32(xs_row[t] - 512u + om1, cur[t]);
-                                    if (row[t] == N - 2) sts_f32(xs_row[t] + 512u + om1, cur[t]);
-                                }
-                            }
-                            if (gs_ok && lane == 31) sts_f32(raw_out + (uint32_t)t * 512u + o, newv);
-                            prev2[t] = cur[t];
-                            prev_up[t] = top;
-                            cur[t] = newv;
-                            __syncwarp();
-                        }
-                    }
-                }
+                general_steps(std::false_type{});
             }
+            TBX_TRACE(3, m);
             if (m >= TBX_BACK && m - TBX_BACK < NC && lane == 0) mbar_arrive(bar_done(m - TBX_BACK));
         }
         if (lane == 0)
@@ -402,7 +514,7 @@ struct TbxJob {
     }
 };
 
-__global__ void __launch_bounds__(LSX_THREADS) k_linsolve_tb(const TbxParams p) {
+__global__ void __launch_bounds__(LSX_THREADS, 5) k_linsolve_tb(const TbxParams p) {
     EQ_DYN_SMEM(tbx_smem_raw);
     const uint32_t sbase = smem_u32(tbx_smem_raw);
     const int total = p.njobs * p.nprob;
@@ -431,6 +543,14 @@ __global__ void __launch_bounds__(LSX_THREADS) k_linsolve_tb(const TbxParams p) 
         const uint32_t jb = p.jobs[t / (unsigned)p.nprob];
         const int g = (int)(jb >> 16), b = (int)(jb & 0xffffu);
         const TbxProblem &pr = p.prob[pi];
+        if (p.jobtimes && threadIdx.x == 0 && pi == 0) {
+            p.jobtimes[4 * ((size_t)g * p.NBP + b)] = lsx_gtime();
+#ifndef EQ_HOST_EMU
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            p.jobtimes[4 * ((size_t)g * p.NBP + b) + 3] = smid;
+#endif
+        }
 #define TBX_DISPATCH(O)                                           \
     {                                                             \
         const TbxJob<O> job(p, pr, sbase, b, g, lane);            \
@@ -443,5 +563,7 @@ __global__ void __launch_bounds__(LSX_THREADS) k_linsolve_tb(const TbxParams p) 
         else if (pr.orient == EQ_ADJUST_COLUMN) TBX_DISPATCH(EQ_ADJUST_COLUMN)
         else TBX_DISPATCH(EQ_PASSIVE)
 #undef TBX_DISPATCH
+        __syncthreads();
+        if (p.jobtimes && threadIdx.x == 0 && pi == 0) p.jobtimes[4 * ((size_t)g * p.NBP + b) + 2] = lsx_gtime();
     }
 }
