@@ -55,7 +55,8 @@ struct TbxParams {
     TbxProblem prob[2];
     int nprob;
     const uint8_t *codes;
-    const uint8_t *chunk_flags;  // [2][NBP][NC]: rows j0-SK-1 .. j0+31 of band b hold a Row ([0]) / Column ([1]) code
+    const uint8_t *chunk_flags;  // [2][NBP][NC]: rows j0-SK-1 .. j0+31 of band b hold [0] a Row code, [1] a Column code other
+                                 // than the UP of row 1 / DOWN of row N-2 every column has (k_build_codes)
     const uint8_t *row_fluid;
     const uint8_t *col_fluid;
     const uint32_t *jobs;        // [G*NBP] (g << 16 | b) in wavefront order
@@ -114,6 +115,14 @@ struct TbxJob {
 #pragma unroll
         for (int d = 0; d <= TBX_BACK; ++d) any |= cflags[m - d];
         return any ? MODE_CODED : MODE_FAST;
+    }
+    // AdjustColumn: may an EDGE macro step use the fast loop (no Column code but the frame-adjacent ones)?
+    __device__ __forceinline__ bool edge_simple(int m) const {
+        if (ORIENT != EQ_ADJUST_COLUMN) return true;
+        unsigned any = 0;
+#pragma unroll
+        for (int d = 0; d <= TBX_BACK; ++d) any |= cflags[min(max(m - d, 0), NC - 1)];
+        return any == 0;
     }
     __device__ __forceinline__ bool need_codes(int q) const {
         if (ORIENT == EQ_PASSIVE) {                                  // row 0 of the code tile carries col_fluid
@@ -320,7 +329,13 @@ struct TbxJob {
         //   carry one) and Passive's frame-column copies.  These steps open and close every job: the band below
         //   cannot start before the first ones are done nor finish before the last, so their duration is the lag
         //   between consecutive bands and the solve is a chain of NB such lags -- they must not be slow.
-        const bool lean_edges = (ORIENT == EQ_ADJUST_ROW) || (ORIENT == EQ_PASSIVE && (!owns_frame_row() || p.passive_fast_frames));
+        const bool lean_edges = (ORIENT != EQ_PASSIVE) || !owns_frame_row() || p.passive_fast_frames;
+        bool col_top[TBX_T], col_bot[TBX_T];
+#pragma unroll
+        for (int t = 0; t < TBX_T; ++t) {
+            col_top[t] = (ORIENT == EQ_ADJUST_COLUMN) && in_row[t] && row[t] == 1;
+            col_bot[t] = (ORIENT == EQ_ADJUST_COLUMN) && in_row[t] && row[t] == N - 2;
+        }
         auto fast_steps = [&](auto zone_c) {
             constexpr int ZONE = decltype(zone_c)::value;
             const int cb = LSX_CW * m_cur - lane;                 // column of sub-step 0 at the first step
@@ -360,6 +375,12 @@ struct TbxJob {
                             const unsigned code = lds_u8(cs_row[t] + (om1 >> 2)) & 3u;
                             F = (code == EQ_CODE_ROW_RIGHT) ? -newv : ((code == EQ_CODE_ROW_LEFT) ? -prev2[t] : cur[t]);
                         }
+                    }
+                    if (ORIENT == EQ_ADJUST_COLUMN) {
+                        // rows 1 and N-2 mirror the frame rows (which AdjustColumn never changes, quirk Q5):
+                        // x[i,1] = -x[i,0] (the `up` this cell was computed with), x[i,N-2] = -x[i,N-1]
+                        const float below = lds_f32(xs_row[t] + 512u + om1);
+                        F = col_top[t] ? -prev_up[t] : (col_bot[t] ? -below : F);
                     }
                     if (fin) sts_f32(xs_row[t] + om1, F);
                     if (ORIENT == EQ_PASSIVE) {
@@ -469,9 +490,9 @@ struct TbxJob {
             const int s_end = min(LSX_CW * m + LSX_CW, S);
             if (nsub == TBX_T && mode == MODE_FAST) {
                 fast_steps(std::integral_constant<int, 0>{});
-            } else if (nsub == TBX_T && mode == MODE_EDGE && lean_edges && LSX_CW * m + LSX_CW - 1 <= N - 2) {
+            } else if (nsub == TBX_T && mode == MODE_EDGE && lean_edges && edge_simple(m) && LSX_CW * m + LSX_CW - 1 <= N - 2) {
                 fast_steps(std::integral_constant<int, 1>{});       // start of the rows only
-            } else if (nsub == TBX_T && mode == MODE_EDGE && lean_edges && LSX_CW * m - 31 - TBX_LAG * (TBX_T - 1) >= 2) {
+            } else if (nsub == TBX_T && mode == MODE_EDGE && lean_edges && edge_simple(m) && LSX_CW * m - 31 - TBX_LAG * (TBX_T - 1) >= 2) {
                 fast_steps(std::integral_constant<int, 2>{});       // end of the rows only
             } else if (mode == MODE_FAST) {
                 // short last group (K not a multiple of TBX_T): same thing with the sub-step count tested
@@ -487,7 +508,12 @@ struct TbxJob {
                             const float x0v = lds_f32(x0_row[t] + o);
                             if (first[t]) up = lds_f32(top_base[t] + o);
                             const float newv = gs_update(x0v, right, cur[t], down, up, a, c_recip);
-                            if (in_row[t]) sts_f32(xs_row[t] + om1, cur[t]);
+                            float F = cur[t];
+                            if (ORIENT == EQ_ADJUST_COLUMN) {
+                                const float below = lds_f32(xs_row[t] + 512u + om1);
+                                F = col_top[t] ? -prev_up[t] : (col_bot[t] ? -below : F);
+                            }
+                            if (in_row[t]) sts_f32(xs_row[t] + om1, F);
                             if (ORIENT == EQ_PASSIVE) {
                                 if (frame_top[t]) sts_f32(xs_row[t] - 512u + om1, cur[t]);
                                 if (frame_bot[t]) sts_f32(xs_row[t] + 512u + om1, cur[t]);

@@ -46,10 +46,18 @@ __global__ void k_build_codes(const uint8_t *__restrict__ cells, uint8_t *__rest
         // the temporally blocked solver uses bands that move up 2 rows per iteration: band b reads the
         // codes of rows 32b-SK .. 32b+32 (SK = 2(T-1)), so a code in row j concerns bands (j-1)/32 .. (j+SK)/32
         const int SK = 2 * (TBX_T - 1), NBP = (L.N - 2 + SK + 31) / 32;
-        if (code & 15u) {
+        // AdjustColumn: the NoWall cells of rows 1 and N-2 always carry UP / DOWN (they touch the frame) and the
+        // solver's fast loop handles exactly that; the flag marks everything else -- a code in another row, or
+        // a cell of those two rows that is a wall or mirrors the other way.
+        bool col_complex = (code & 12u) != 0;
+        if (i >= 1 && i <= L.N - 2) {
+            if (j == 1) col_complex = (code & (12u | EQ_CODE_WALL)) != EQ_CODE_COL_UP;
+            else if (j == L.N - 2) col_complex = (code & (12u | EQ_CODE_WALL)) != EQ_CODE_COL_DOWN;
+        }
+        if ((code & 3u) || col_complex) {
             for (int bb = (j - 1) / 32; bb <= min((j + SK) / 32, NBP - 1); ++bb) {
                 if (code & 3u) chunk_flags_tb[(size_t)bb * NC + i / EQ_LSX_CW] = 1;
-                if (code & 12u) chunk_flags_tb[(size_t)NBP * NC + (size_t)bb * NC + i / EQ_LSX_CW] = 1;
+                if (col_complex) chunk_flags_tb[(size_t)NBP * NC + (size_t)bb * NC + i / EQ_LSX_CW] = 1;
             }
         }
         const bool owned = (j >= L.row0 && j < L.row1);   // the sparse lists drive stand-alone boundary passes

@@ -31,6 +31,15 @@ def test_lin_solve_exact_last_band_under_skew(oracle, emu_lib, orient, n, k):
     P.check_lin_solve(oracle, emu_lib, n, k, [(n - 12, 3, n - 1, 9), (5, n - 6, 40, n - 1), (30, 30, 36, 66)], orient)
 
 
+@pytest.mark.parametrize("orient", [P.ROW, P.COL, P.PASSIVE])
+def test_lin_solve_exact_obstacles_touching_the_frame(oracle, emu_lib, orient):
+    # Rows 1 / N-2 and columns 1 / N-2 normally hold plain frame-adjacent fix-ups, which the fast loops take
+    # in their stride; obstacles glued to each side of the frame break that pattern for some chunks only.
+    n = 200
+    rects = [(50, 1, 70, 4), (120, n - 5, 150, n - 1), (1, 90, 6, 120), (n - 4, 20, n - 1, 60), (100, 100, 104, 104)]
+    P.check_lin_solve(oracle, emu_lib, n, 4, rects, orient)
+
+
 @pytest.mark.parametrize("n,k", [(98, 4), (131, 3)])
 def test_lin_solve_passive_with_a_walled_off_column(oracle, emu_lib, n, k):
     # An obstacle spanning the full height leaves columns without a NoWall cell: their frame-row
