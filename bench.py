@@ -287,7 +287,9 @@ def main():
         if rec:   # per launch like `achieved`: one launch solves 1 or 2 fields (5 solves in 4 launches per frame)
             traffic = rec["dram_bytes_per_solve"] * 5.0 * prof["steps"] / wave_launches
     roofline = {
-        "bound": "hbm", "kernel": "k_linsolve_exact (wavefront Gauss-Seidel, all K iterations per launch)",
+        "bound": "hbm",
+        "kernel": ("k_linsolve_tb (wavefront Gauss-Seidel, 2 iterations fused per job, all K iterations per launch)"
+                   if world == 1 else "k_linsolve_exact (row-slab wavefront Gauss-Seidel, all K iterations per launch)"),
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
         "peak_source": peak_src, "per": "GPU (rank 0)" if world > 1 else "GPU",
         "algorithmic_bytes_per_launch": ls_bytes / wave_launches,
