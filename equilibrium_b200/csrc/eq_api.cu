@@ -494,6 +494,14 @@ static int get_tb_job_table(eq_fluid *h, int G, const uint32_t **out) {
 }
 
 static int lin_solve_exact_tb(eq_fluid *h, const LinSolveReq *req, int nreq, int64_t iters) {
+    // Two independent solves (the velocity diffusions) can share one launch, but measured on 16384^2 K=20 the
+    // shared launch takes 53.9 ms against 16.6 + 19.0 ms back to back: each problem gets half of the resident
+    // CTAs while its band-to-band chain stays as long, and two orientations' loops compete for the
+    // instruction cache.  One launch per field unless EQ_TB_BATCH=1.
+    if (nreq > 1 && !env_int("EQ_TB_BATCH", 0)) {
+        for (int i = 0; i < nreq; ++i) TRY(lin_solve_exact_tb(h, req + i, 1, iters));
+        return EQ_OK;
+    }
     const EqLayout L = h->L;
     const int NBP = (L.N - 2 + TBX_SK + 31) / 32;
     const int NC = (L.N + EQ_LSX_CW - 1) / EQ_LSX_CW;
@@ -604,9 +612,11 @@ static int lin_solve(eq_fluid *h, const LinSolveReq *req, int nreq, int64_t iter
         ProfScope ps(h, CAT_LS, (int)(((iters + RB_T - 1) / RB_T + 1) * nreq));
         return lin_solve_red_black(h, req, nreq, iters);
     }
-    ProfScope ps(h, CAT_LS, (int)((iters + LSX_KMAX - 1) / LSX_KMAX) + nreq);
     static const bool tb_off = getenv("EQ_LSX_TB") && atoi(getenv("EQ_LSX_TB")) == 0;
-    if (h->world == 1 && TBX_T > 1 && !tb_off) return lin_solve_exact_tb(h, req, nreq, iters);
+    const bool use_tb = (h->world == 1 && TBX_T > 1 && !tb_off);
+    const int wave_launches = (int)((iters + LSX_KMAX - 1) / LSX_KMAX) * ((use_tb && !env_int("EQ_TB_BATCH", 0)) ? nreq : 1);
+    ProfScope ps(h, CAT_LS, wave_launches + nreq);     // + one corner kernel per field
+    if (use_tb) return lin_solve_exact_tb(h, req, nreq, iters);
     return lin_solve_exact(h, req, nreq, iters);
 }
 
