@@ -177,6 +177,11 @@ static int prof_collect(eq_fluid *h) {
 static inline dim3 row_grid(const eq_fluid *h, int rows, int threads = 256) {
     return dim3((unsigned)((h->L.N + threads - 1) / threads), (unsigned)rows, 1);
 }
+// k_divergence / k_gradient: a block covers 4 * EQ_ST_THREADS columns x EQ_ST_ROWS rows
+static inline dim3 stencil_grid(const eq_fluid *h, int rows) {
+    const int cols_per_block = 4 * EQ_ST_THREADS;
+    return dim3((unsigned)((h->L.N + cols_per_block - 1) / cols_per_block), (unsigned)((rows + EQ_ST_ROWS - 1) / EQ_ST_ROWS), 1);
+}
 static int check_launch(const char *what);
 // rows of the interior (1..N-2) that this rank owns
 static inline int owned_interior_rows(const eq_fluid *h) {
@@ -579,7 +584,12 @@ static int lin_solve_exact_tb(eq_fluid *h, const LinSolveReq *req, int nreq, int
 static int lin_solve_red_black(eq_fluid *h, const LinSolveReq *req, int nreq, int64_t iters) {
     const EqLayout L = h->L;
     const int rows = L.row1 - L.row0;
-    const dim3 grid((unsigned)((L.N + RB_TW - 1) / RB_TW), (unsigned)((rows + RB_TH - 1) / RB_TH), 1);
+    // EQ_RB_KERNEL=tiled selects the older shared-memory kernel (A/B runs); the default keeps the tile in registers
+    static const bool use_tiled = getenv("EQ_RB_KERNEL") && !strcmp(getenv("EQ_RB_KERNEL"), "tiled");
+    const dim3 grid_t((unsigned)((L.N + RB_TW - 1) / RB_TW), (unsigned)((rows + RB_TH - 1) / RB_TH), 1);
+    // k_rb_reg: tiles on a fixed lattice of RBR_WO x RBR_HO outputs; this rank runs the tile rows that meet its slab
+    const int ty0 = L.row0 / RBR_HO, ty1 = (L.row1 - 1) / RBR_HO;
+    const dim3 grid_r((unsigned)((L.N + RBR_WO - 1) / RBR_WO), (unsigned)(ty1 - ty0 + 1), 1);
     for (int i = 0; i < nreq; ++i) {
         const float c_recip = 1.0f / req[i].c;
         float *cur = req[i].x, *other = h->rb_tmp;
@@ -588,9 +598,16 @@ static int lin_solve_red_black(eq_fluid *h, const LinSolveReq *req, int nreq, in
         for (int64_t done = 0; done < iters; done += RB_T) {
             const int it = (int)std::min<int64_t>(RB_T, iters - done);
             TRY(halo_xchg(h, cur, RB_H));
-            EQ_LAUNCH(k_rb_tiled, grid, RB_THREADS, RB_SMEM_BYTES, h->stream, cur, other, req[i].x0, h->codes,
-                      h->row_fluid, h->col_fluid, req[i].a, c_recip, req[i].orient, it, L.row0, L.row1, L);
-            TRY(check_launch("k_rb_tiled"));
+            if (use_tiled) {
+                EQ_LAUNCH(k_rb_tiled, grid_t, RB_THREADS, RB_SMEM_BYTES, h->stream, cur, other, req[i].x0, h->codes,
+                          h->row_fluid, h->col_fluid, req[i].a, c_recip, req[i].orient, it, L.row0, L.row1, L);
+                TRY(check_launch("k_rb_tiled"));
+            } else {
+                EQ_LAUNCH(k_rb_reg, grid_r, RBR_THREADS, RBR_SMEM_BYTES, h->stream, cur, other, req[i].x0, h->codes,
+                          h->chunk_flags, h->row_fluid, h->col_fluid, req[i].a, c_recip, req[i].orient, it, L.row0, L.row1,
+                          ty0, L);
+                TRY(check_launch("k_rb_reg"));
+            }
             std::swap(cur, other);
         }
         if (cur != req[i].x)
@@ -635,7 +652,7 @@ static int project(eq_fluid *h, float *vx, float *vy, float *p, float *div, int6
     TRY(halo_xchg(h, vy));                                             // the stencil reads vy[j-1], vy[j+1]
     {
         ProfScope ps(h, CAT_PROJ, 1);
-        EQ_LAUNCH(k_divergence, row_grid(h, owned_interior_rows(h)), 256, 0, h->stream, vx, vy, div, p, L);
+        EQ_LAUNCH(k_divergence, stencil_grid(h, owned_interior_rows(h)), EQ_ST_THREADS, 0, h->stream, vx, vy, div, p, L);
         TRY(check_launch("k_divergence"));
     }
     TRY(set_boundaries(h, EQ_PASSIVE, div));                           // :351
@@ -644,7 +661,7 @@ static int project(eq_fluid *h, float *vx, float *vy, float *p, float *div, int6
     TRY(lin_solve(h, &r, 1, iters));                                   // :353-362
     {
         ProfScope ps(h, CAT_PROJ, 1);
-        EQ_LAUNCH(k_gradient, row_grid(h, owned_interior_rows(h)), 256, 0, h->stream, vx, vy, p, L);
+        EQ_LAUNCH(k_gradient, stencil_grid(h, owned_interior_rows(h)), EQ_ST_THREADS, 0, h->stream, vx, vy, p, L);
         TRY(check_launch("k_gradient"));
     }
     TRY(set_boundaries(h, EQ_ADJUST_ROW, vx));                         // :373
@@ -661,9 +678,9 @@ static int advect(eq_fluid *h, int orientA, float *dA, const float *d0A, int ori
         ProfScope ps(h, CAT_ADV, 1);
         const EqPeerTable tA = peer_table(h, d0A), tB = peer_table(h, d0B);
         if (dB)
-            EQ_LAUNCH((k_advect<2>), owned_interior_rows(h), 256, 16, h->stream, dA, tA, dB, tB, vx, vy, h->prm.delta_t, L);
+            EQ_LAUNCH((k_advect<2>), owned_interior_rows(h), EQ_ADV_THREADS, 16, h->stream, dA, tA, dB, tB, vx, vy, h->prm.delta_t, L);
         else
-            EQ_LAUNCH((k_advect<1>), owned_interior_rows(h), 256, 16, h->stream, dA, tA, nullptr, tB, vx, vy, h->prm.delta_t, L);
+            EQ_LAUNCH((k_advect<1>), owned_interior_rows(h), EQ_ADV_THREADS, 16, h->stream, dA, tA, nullptr, tB, vx, vy, h->prm.delta_t, L);
         TRY(check_launch("k_advect"));
     }
     TRY(barrier_all(h));     // ... and nobody may overwrite d0 while a neighbour still samples it
@@ -799,6 +816,7 @@ static int alloc_handle(const EqParams *params, eq_fluid **out) {
     h->peer_sync[h->rank] = h->sync;
     CU(cudaFuncSetAttribute(k_linsolve_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LSX_SMEM_BYTES));
     CU(cudaFuncSetAttribute(k_rb_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RB_SMEM_BYTES));
+    CU(cudaFuncSetAttribute(k_rb_reg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RBR_SMEM_BYTES));
     int per_sm = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_linsolve_exact, LSX_THREADS, LSX_SMEM_BYTES));
     h->lsx_ctas = std::max(1, per_sm) * h->sm_count;

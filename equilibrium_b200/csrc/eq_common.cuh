@@ -57,6 +57,7 @@ struct EqPeerTable {
     int world;
 };
 __device__ __forceinline__ const float *eq_owner_base(const EqPeerTable &t, unsigned j) {
+    if (t.world <= 1) return t.base[0];
     int r = 0;
 #pragma unroll
     for (int i = 1; i < EQ_MAX_RANKS; ++i)

@@ -14,6 +14,7 @@
 // another tile's output).
 #pragma once
 #include "eq_common.cuh"
+#include <type_traits>
 
 #define RB_T 4
 #define RB_H (3 * RB_T)
@@ -147,5 +148,247 @@ __global__ void __launch_bounds__(RB_THREADS) k_rb_tiled(const float *__restrict
         const int ty = p / RB_TW, tx = p - ty * RB_TW;
         const int gx = gx0 + RB_H + tx, gy = gy0 + RB_H + ty;
         if (gx < N && gy < N && gy >= row_lo && gy < row_hi) xout[(size_t)gx + (size_t)gy * P] = xs[(ty + RB_H) * RB_RW + tx + RB_H];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_rb_reg: the temporally blocked red-black solver with the tile held in REGISTERS.
+//
+// k_rb_tiled keeps its region in shared memory and pays 5 LDS + 1 STS (2-way bank conflicts: same-colour
+// cells are 2 floats apart) per cell update: it is bound by the shared-memory issue rate, 5x above the HBM
+// time of a pass.  Here a thread owns one column PAIR (an even and an odd column) over all RBR_H rows of the
+// tile: 2 x 64 floats in registers.  For the cell of colour c in row y (element e = (c ^ y) & 1 of the pair,
+// static once the row loop is unrolled: tile origins are even in both axes)
+//     up / down            = the same element of rows y-1 / y+1      (own registers)
+//     one horizontal side  = the other element of the pair           (own register)
+//     the other side       = the neighbouring lane's other element   (one SHFL; across the 4 warps of a
+//                            CTA through a 2 KB edge buffer in shared memory, lanes 0 / 31 only)
+//     x0                   = a thread-private, conflict-free shared-memory slot (register spill space)
+// so an update is 1 SHFL + 1 LDS + 6 FP.  set_boundaries runs on the same registers from a packed 4-bit
+// direction code per cell (LEFT / RIGHT / UP / DOWN mirror; Passive's conditional frame copies are turned
+// into the same codes with sign +), and only in tiles that hold a code at all.
+//
+// Tiles sit on a fixed lattice (output RBR_WO x RBR_HO cells, halo 3 cells per iteration on every side);
+// passes ping-pong between two arrays exactly like k_rb_tiled.  Bit-identical to it and to the oracle's
+// red-black restatement (ref_lin_solve_red_black): same expression tree, same sweep order.
+// ---------------------------------------------------------------------------------------------
+#define RBR_T RB_T
+#define RBR_HALO RB_H                       // 12
+#define RBR_WARPS 4
+#define RBR_THREADS (32 * RBR_WARPS)
+#define RBR_W (64 * RBR_WARPS)              // 256 columns per CTA
+#define RBR_H 64                            // rows per CTA, all of them in registers
+#define RBR_WO (RBR_W - 2 * RBR_HALO)       // 232
+#define RBR_HO (RBR_H - 2 * RBR_HALO)       // 40
+#define RBR_X0_BYTES (2u * RBR_H * RBR_THREADS * 4u)
+#define RBR_EDGE_OFF RBR_X0_BYTES           // float edge[RBR_WARPS][2][RBR_H]
+#define RBR_SMEM_BYTES (RBR_X0_BYTES + RBR_WARPS * 2u * RBR_H * 4u)
+
+#define RBR_DIR_LEFT 1u
+#define RBR_DIR_RIGHT 2u
+#define RBR_DIR_UP 3u
+#define RBR_DIR_DOWN 4u
+
+__global__ void __launch_bounds__(RBR_THREADS, 2) k_rb_reg(const float *__restrict__ xin, float *__restrict__ xout,
+                                                           const float *__restrict__ x0, const uint8_t *__restrict__ codes,
+                                                           const uint8_t *__restrict__ chunk_flags,
+                                                           const uint8_t *__restrict__ row_fluid,
+                                                           const uint8_t *__restrict__ col_fluid, float a, float c_recip,
+                                                           int orient, int iters, int row_lo, int row_hi, int tile_y0,
+                                                           EqLayout L) {
+    EQ_DYN_SMEM(rbr_smem);
+    float *x0s = reinterpret_cast<float *>(rbr_smem);                    // [2][RBR_H][RBR_THREADS], thread-private slots
+    float *edge = reinterpret_cast<float *>(rbr_smem + RBR_EDGE_OFF);     // [warp][side][row]
+    const int N = L.N, P = L.P;
+    const int tid = (int)threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int gx0 = (int)blockIdx.x * RBR_WO - RBR_HALO;                 // even
+    const int gy0 = (tile_y0 + (int)blockIdx.y) * RBR_HO - RBR_HALO;     // even
+    const int lx = 64 * w + 2 * lane, gx = gx0 + lx;                     // my even column
+    const bool in0 = (gx >= 0 && gx < N), in1 = (gx + 1 >= 0 && gx + 1 < N);
+    const bool colok0 = (gx >= 1 && gx <= N - 2), colok1 = (gx + 1 >= 1 && gx + 1 <= N - 2);
+
+    float v[RBR_H][2];
+    // ---- stage: x into registers, x0 into my shared-memory slots ----
+#pragma unroll
+    for (int y = 0; y < RBR_H; ++y) {
+        const int gy = gy0 + y;
+        float2 xv = make_float2(0.f, 0.f), x0v = make_float2(0.f, 0.f);
+        if (gy >= 0 && gy < N) {
+            const size_t o = (size_t)gy * P + gx;                        // only dereferenced where in0 / in1
+            if (in0 && in1) {
+                xv = *reinterpret_cast<const float2 *>(xin + o);
+                x0v = *reinterpret_cast<const float2 *>(x0 + o);
+            } else {
+                if (in0) { xv.x = xin[o]; x0v.x = x0[o]; }
+                if (in1) { xv.y = xin[o + 1]; x0v.y = x0[o + 1]; }
+            }
+        }
+        v[y][0] = xv.x;
+        v[y][1] = xv.y;
+        x0s[(0 * RBR_H + y) * RBR_THREADS + tid] = x0v.x;
+        x0s[(1 * RBR_H + y) * RBR_THREADS + tid] = x0v.y;
+    }
+    // ---- does set_boundaries have anything to do in this tile? ----
+    bool need_fix;
+    if (orient == EQ_PASSIVE) {
+        need_fix = (gx0 <= 0) || (gy0 <= 0) || (gx0 + RBR_W >= N) || (gy0 + RBR_H >= N);
+    } else {
+        // (band, chunk) summaries of k_build_codes: band = (row-1)/32, chunk = column / EQ_LSX_CW; a superset is fine
+        const int NB = (N - 2 + 31) / 32, NC = (N + EQ_LSX_CW - 1) / EQ_LSX_CW;
+        const int b_lo = max((max(gy0, 1) - 1) / 32 - 1, 0), b_hi = min((min(gy0 + RBR_H - 1, N - 2) - 1) / 32 + 1, NB - 1);
+        const int q_lo = max(gx0, 0) / EQ_LSX_CW, q_hi = min(gx0 + RBR_W - 1, N - 1) / EQ_LSX_CW;
+        const uint8_t *fl = chunk_flags + (orient == EQ_ADJUST_COLUMN ? (size_t)NB * NC : 0);
+        const int nq = q_hi - q_lo + 1, total = max(b_hi - b_lo + 1, 0) * max(nq, 0);
+        int any = 0;
+        for (int t = tid; t < total; t += RBR_THREADS) any |= fl[(size_t)(b_lo + t / nq) * NC + q_lo + t % nq];
+        need_fix = __syncthreads_or(any) != 0;
+    }
+    // packed direction codes: 4 bits per cell, cell (y, e) at bits 8*(y&3) + 4*e of cw[y>>2]
+    uint32_t cw[RBR_H / 4];
+#pragma unroll
+    for (int i = 0; i < RBR_H / 4; ++i) cw[i] = 0u;
+    if (need_fix) {
+#pragma unroll
+        for (int y = 0; y < RBR_H; ++y) {
+            const int gy = gy0 + y;
+            unsigned d0 = 0u, d1 = 0u;
+            if (gy >= 0 && gy < N) {
+                if (orient == EQ_PASSIVE) {
+                    // frame cells copy their interior neighbour (fluid.rs:182-186, conditional per quirk Q6)
+                    const bool fy = (gy == 0 || gy == N - 1);
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int cx = gx + e;
+                        unsigned d = 0u;
+                        if (cx >= 0 && cx < N) {
+                            const bool fx = (cx == 0 || cx == N - 1);
+                            if (fy && !fx) { if (col_fluid[cx]) d = (gy == 0) ? RBR_DIR_DOWN : RBR_DIR_UP; }
+                            else if (fx && !fy) { if (row_fluid[gy]) d = (cx == 0) ? RBR_DIR_RIGHT : RBR_DIR_LEFT; }
+                        }
+                        if (e == 0) d0 = d; else d1 = d;
+                    }
+                } else {
+                    const size_t o = (size_t)gy * P + gx;
+                    const unsigned c0 = in0 ? codes[o] : 0u, c1 = in1 ? codes[o + 1] : 0u;
+                    if (orient == EQ_ADJUST_ROW) {
+                        d0 = c0 & 3u;                                     // 1 LEFT, 2 RIGHT
+                        d1 = c1 & 3u;
+                    } else {
+                        d0 = (c0 >> 2) & 3u;                              // 1 UP, 2 DOWN
+                        d1 = (c1 >> 2) & 3u;
+                        d0 = d0 ? d0 + 2u : 0u;
+                        d1 = d1 ? d1 + 2u : 0u;
+                    }
+                }
+            }
+            cw[y >> 2] |= (d0 | (d1 << 4)) << (8 * (y & 3));
+        }
+    }
+    const bool negate = (orient != EQ_PASSIVE);                           // AdjustRow / AdjustColumn mirror with a sign flip
+    // rows that are interior rows of the grid (uniform over the CTA)
+    unsigned long long rowmask = 0ull;
+#pragma unroll
+    for (int y = 0; y < RBR_H; ++y)
+        if (gy0 + y >= 1 && gy0 + y <= N - 2) rowmask |= 1ull << y;
+    const bool guard = !(gx0 >= 1 && gx0 + RBR_W - 1 <= N - 2 && gy0 >= 1 && gy0 + RBR_H - 1 <= N - 2);
+    float *my_edge_l = edge + (w * 2 + 0) * RBR_H;                         // lane 0 publishes its even column here
+    float *my_edge_r = edge + (w * 2 + 1) * RBR_H;                         // lane 31 its odd column
+    const float *nb_edge_l = edge + ((max(w, 1) - 1) * 2 + 1) * RBR_H;     // right edge of the warp to my left
+    const float *nb_edge_r = edge + (min(w + 1, RBR_WARPS - 1) * 2 + 0) * RBR_H;   // left edge of the warp to my right
+    const bool has_l = (w > 0), has_r = (w < RBR_WARPS - 1);
+
+#pragma unroll
+    for (int y = 0; y < RBR_H; ++y) {
+        if (lane == 0) my_edge_l[y] = v[y][0];
+        if (lane == 31) my_edge_r[y] = v[y][1];
+    }
+    __syncthreads();
+
+    // one half-sweep: the cells of colour c.  Everything a cell reads has the other colour.
+    auto sweep = [&](auto colour_c, auto guard_c) {
+        constexpr int C = decltype(colour_c)::value;
+        constexpr bool GUARD = decltype(guard_c)::value;
+#pragma unroll
+        for (int y = 1; y <= RBR_H - 2; ++y) {
+            const int e = (C ^ y) & 1;
+            float left, right;
+            if (e == 0) {
+                float hn = __shfl_up_sync(0xffffffffu, v[y][1], 1);
+                if (lane == 0 && has_l) hn = nb_edge_l[y];
+                left = hn;
+                right = v[y][1];
+            } else {
+                float hn = __shfl_down_sync(0xffffffffu, v[y][0], 1);
+                if (lane == 31 && has_r) hn = nb_edge_r[y];
+                left = v[y][0];
+                right = hn;
+            }
+            const float nv = gs_update(x0s[(e * RBR_H + y) * RBR_THREADS + tid], right, left, v[y + 1][e], v[y - 1][e], a, c_recip);
+            if (GUARD) {
+                const bool ok = (e == 0 ? colok0 : colok1) && ((rowmask >> y) & 1ull);
+                v[y][e] = ok ? nv : v[y][e];
+            } else {
+                v[y][e] = nv;
+            }
+            if (e == 0) { if (lane == 0) my_edge_l[y] = v[y][0]; }
+            else { if (lane == 31) my_edge_r[y] = v[y][1]; }
+        }
+    };
+
+    for (int it = 0; it < iters; ++it) {
+        if (guard) sweep(std::integral_constant<int, 0>{}, std::true_type{});
+        else sweep(std::integral_constant<int, 0>{}, std::false_type{});
+        __syncthreads();
+        if (guard) sweep(std::integral_constant<int, 1>{}, std::true_type{});
+        else sweep(std::integral_constant<int, 1>{}, std::false_type{});
+        __syncthreads();
+        if (need_fix) {
+            // ---- set_boundaries (fluid.rs:252-272) on the registers.  Sources (wall cells; interior cells for
+            // Passive) are never destinations, so the order inside the pass does not matter.
+#pragma unroll
+            for (int y = 0; y < RBR_H; ++y) {
+                float ln = __shfl_up_sync(0xffffffffu, v[y][1], 1);       // left neighbour of my even cell
+                float rn = __shfl_down_sync(0xffffffffu, v[y][0], 1);     // right neighbour of my odd cell
+                const unsigned byte = (cw[y >> 2] >> (8 * (y & 3))) & 0xffu;
+                if (byte) {
+                    if (lane == 0) ln = has_l ? nb_edge_l[y] : v[y][0];
+                    if (lane == 31) rn = has_r ? nb_edge_r[y] : v[y][1];
+                    const unsigned d0 = byte & 15u, d1 = byte >> 4;
+                    const float up0 = v[y > 0 ? y - 1 : y][0], dn0 = v[y < RBR_H - 1 ? y + 1 : y][0];
+                    const float up1 = v[y > 0 ? y - 1 : y][1], dn1 = v[y < RBR_H - 1 ? y + 1 : y][1];
+                    const bool edge_l = (lane == 0 && !has_l), edge_r = (lane == 31 && !has_r);
+                    if (d0) {
+                        const float s = (d0 == RBR_DIR_LEFT) ? ln : (d0 == RBR_DIR_RIGHT) ? v[y][1] : (d0 == RBR_DIR_UP) ? up0 : dn0;
+                        const bool valid = !((d0 == RBR_DIR_LEFT && edge_l) || (d0 == RBR_DIR_UP && y == 0) || (d0 == RBR_DIR_DOWN && y == RBR_H - 1));
+                        if (valid) v[y][0] = negate ? -s : s;
+                    }
+                    if (d1) {
+                        const float s = (d1 == RBR_DIR_LEFT) ? v[y][0] : (d1 == RBR_DIR_RIGHT) ? rn : (d1 == RBR_DIR_UP) ? up1 : dn1;
+                        const bool valid = !((d1 == RBR_DIR_RIGHT && edge_r) || (d1 == RBR_DIR_UP && y == 0) || (d1 == RBR_DIR_DOWN && y == RBR_H - 1));
+                        if (valid) v[y][1] = negate ? -s : s;
+                    }
+                }
+            }
+            if (it + 1 < iters) {
+#pragma unroll
+                for (int y = 0; y < RBR_H; ++y) {
+                    if (lane == 0) my_edge_l[y] = v[y][0];
+                    if (lane == 31) my_edge_r[y] = v[y][1];
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // ---- write the centre ----
+    if (lx >= RBR_HALO && lx < RBR_W - RBR_HALO && in0) {
+#pragma unroll
+        for (int y = RBR_HALO; y < RBR_H - RBR_HALO; ++y) {
+            const int gy = gy0 + y;
+            if (gy >= row_lo && gy < row_hi && gy < N) {
+                const size_t o = (size_t)gy * P + gx;
+                if (in1) *reinterpret_cast<float2 *>(xout + o) = make_float2(v[y][0], v[y][1]);
+                else xout[o] = v[y][0];
+            }
+        }
     }
 }

@@ -351,37 +351,55 @@ struct TbxJob {
             }
 #pragma unroll
             for (int i = 0; i < LSX_CW; ++i) {
+                // Phase A: the shuffles and the operand fetches of BOTH sub-steps, back to back.  Nothing a sub-step
+                // stores in this step is read by the other one before the next step (its inputs were finalised at
+                // least one step earlier, see the header), so the T dependency chains SHFL -> FADD, FMUL, FADD, FMUL
+                // are independent inside a step and the scheduler interleaves them -- as long as no volatile
+                // shared-memory access of sub-step t sits between the arithmetic of t and the shuffle of t+1.
+                float up[TBX_T], right_n[TBX_T], down_n[TBX_T], x0_n[TBX_T], self[TBX_T], below[TBX_T];
+                unsigned code[TBX_T];
+#pragma unroll
+                for (int t = 0; t < TBX_T; ++t) up[t] = __shfl_up_sync(0xffffffffu, cur[t], 1);
+#pragma unroll
+                for (int t = 0; t < TBX_T; ++t) {
+                    const uint32_t o = (ob + 4u * i - 4u * TBX_LAG * t) & 508u;
+                    const uint32_t o1 = (o + 4u) & 508u, o2 = (o + 8u) & 508u, om1 = (o - 4u) & 508u;
+                    right_n[t] = lds_f32(xs_row[t] + o2);
+                    down_n[t] = lds_f32(down_row[t] + o1);
+                    x0_n[t] = lds_f32(x0_row[t] + o1);
+                    if (first[t]) {
+                        up[t] = topv[t];
+                        topv[t] = lds_f32(top_base[t] + o1);
+                    }
+                    self[t] = 0.f;
+                    code[t] = 0u;
+                    below[t] = 0.f;
+                    if (ZONE != 0) {
+                        self[t] = lds_f32(xs_row[t] + o);
+                        if (ORIENT == EQ_ADJUST_ROW) code[t] = lds_u8(cs_row[t] + (om1 >> 2)) & 3u;
+                    }
+                    // rows 1 and N-2 mirror the frame rows (which AdjustColumn never changes, quirk Q5):
+                    // x[i,1] = -x[i,0] (the `up` this cell was computed with), x[i,N-2] = -x[i,N-1]
+                    if (ORIENT == EQ_ADJUST_COLUMN) below[t] = lds_f32(xs_row[t] + 512u + om1);
+                }
+                // Phase B: arithmetic and the stores of the step
 #pragma unroll
                 for (int t = 0; t < TBX_T; ++t) {
                     const int c = cb + i - TBX_LAG * t;
                     const uint32_t o = (ob + 4u * i - 4u * TBX_LAG * t) & 508u;
-                    const uint32_t o1 = (o + 4u) & 508u, o2 = (o + 8u) & 508u, om1 = (o - 4u) & 508u;
-                    float up = __shfl_up_sync(0xffffffffu, cur[t], 1);
-                    if (first[t]) up = topv[t];
-                    const float right_n = lds_f32(xs_row[t] + o2);
-                    const float down_n = lds_f32(down_row[t] + o1);
-                    const float x0_n = lds_f32(x0_row[t] + o1);
-                    if (first[t]) topv[t] = lds_f32(top_base[t] + o1);
-                    float newv = gs_update(x0v[t], right[t], cur[t], down[t], up, a, c_recip);
+                    const uint32_t om1 = (o - 4u) & 508u;
+                    float newv = gs_update(x0v[t], right[t], cur[t], down[t], up[t], a, c_recip);
                     bool interior = in_row[t], fin = in_row[t];
                     float F = cur[t];
                     if (ZONE != 0) {
-                        const float self = lds_f32(xs_row[t] + o);
                         const bool frame_col = in_row[t] & (ZONE == 1 ? (c == 0) : (c == N - 1));
                         interior = in_row[t] & (ZONE == 1 ? (c >= 1) : (c <= N - 2));
                         fin = in_row[t] & (ZONE == 1 ? (c >= 2) : (c <= N - 1));        // cf = c-1 in 1 .. N-2
-                        newv = interior ? newv : (frame_col ? self : cur[t]);
-                        if (ORIENT == EQ_ADJUST_ROW) {
-                            const unsigned code = lds_u8(cs_row[t] + (om1 >> 2)) & 3u;
-                            F = (code == EQ_CODE_ROW_RIGHT) ? -newv : ((code == EQ_CODE_ROW_LEFT) ? -prev2[t] : cur[t]);
-                        }
+                        newv = interior ? newv : (frame_col ? self[t] : cur[t]);
+                        if (ORIENT == EQ_ADJUST_ROW)
+                            F = (code[t] == EQ_CODE_ROW_RIGHT) ? -newv : ((code[t] == EQ_CODE_ROW_LEFT) ? -prev2[t] : cur[t]);
                     }
-                    if (ORIENT == EQ_ADJUST_COLUMN) {
-                        // rows 1 and N-2 mirror the frame rows (which AdjustColumn never changes, quirk Q5):
-                        // x[i,1] = -x[i,0] (the `up` this cell was computed with), x[i,N-2] = -x[i,N-1]
-                        const float below = lds_f32(xs_row[t] + 512u + om1);
-                        F = col_top[t] ? -prev_up[t] : (col_bot[t] ? -below : F);
-                    }
+                    if (ORIENT == EQ_ADJUST_COLUMN) F = col_top[t] ? -prev_up[t] : (col_bot[t] ? -below[t] : F);
                     if (fin) sts_f32(xs_row[t] + om1, F);
                     if (ORIENT == EQ_PASSIVE) {
                         // fluid.rs:182-186 (every col_fluid is set here: passive_fast_frames)
@@ -392,13 +410,13 @@ struct TbxJob {
                     }
                     if (interior & (lane == 31)) sts_f32(raw_out + (uint32_t)t * 512u + o, newv);
                     prev2[t] = cur[t];
-                    prev_up[t] = up;
+                    prev_up[t] = up[t];
                     cur[t] = newv;
-                    right[t] = right_n;
-                    down[t] = down_n;
-                    x0v[t] = x0_n;
-                    __syncwarp();
+                    right[t] = right_n[t];
+                    down[t] = down_n[t];
+                    x0v[t] = x0_n[t];
                 }
+                __syncwarp();
             }
         };
 

@@ -156,41 +156,123 @@ __global__ void k_bnd_passive(float *x, const uint8_t *__restrict__ row_fluid,
 
 // ---------------------------------------------------------------------------
 // project, part 1 (fluid.rs:339-349): divergence and p = 0 on the interior.
+//
+// HBM-bound streaming stencils (16 and 20 algorithmic bytes per cell).  A thread owns one
+// 16-byte column group (4 cells) and walks EQ_ST_ROWS consecutive rows: every global access is a
+// coalesced 128-bit load or store, and the rows above / below (vy for the divergence, p for the
+// gradient) roll through registers, so each element is requested once per block row instead of
+// three times.  The horizontal neighbours of the group's end cells are two scalar loads that hit
+// the L1 lines the neighbouring lanes fetch.  The frame columns 0 / N-1 and the pad columns are
+// never written: the two groups that contain them fall back to predicated scalar stores.
 // ---------------------------------------------------------------------------
-__global__ void k_divergence(const float *__restrict__ vx, const float *__restrict__ vy,
-                             float *__restrict__ div, float *__restrict__ p, EqLayout L) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int j = blockIdx.y + max(L.row0, 1);              // owned interior rows
-    if (i < 1 || i > L.N - 2) return;
-    const size_t o = (size_t)i + (size_t)j * L.P;
-    float t = __fsub_rn(vx[o + 1], vx[o - 1]);
-    t = __fadd_rn(t, vy[o + L.P]);
-    t = __fsub_rn(t, vy[o - L.P]);
-    div[o] = __fdiv_rn(__fmul_rn(-0.5f, t), (float)L.N);
-    p[o] = 0.0f;
+#define EQ_ST_ROWS 8        // rows per thread
+#define EQ_ST_THREADS 128   // one block covers 512 columns x EQ_ST_ROWS rows
+
+__device__ __forceinline__ float4 ldg_f4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+__device__ __forceinline__ void stg_f4(float *p, const float4 &v) { *reinterpret_cast<float4 *>(p) = v; }
+// store the cells of a column group that lie on interior columns 1 .. N-2
+__device__ __forceinline__ void eq_store_group(float *dst, int i0, int N, const float4 &v) {
+    if (i0 >= 1 && i0 + 3 <= N - 2) {
+        stg_f4(dst, v);
+    } else {
+        if (i0 >= 1 && i0 <= N - 2) dst[0] = v.x;
+        if (i0 + 1 >= 1 && i0 + 1 <= N - 2) dst[1] = v.y;
+        if (i0 + 2 <= N - 2) dst[2] = v.z;
+        if (i0 + 3 <= N - 2) dst[3] = v.w;
+    }
+}
+
+__device__ __forceinline__ float eq_div_cell(float vx_r, float vx_l, float vy_d, float vy_u, float nf) {
+    float t = __fsub_rn(vx_r, vx_l);                                   // :341-345
+    t = __fadd_rn(t, vy_d);
+    t = __fsub_rn(t, vy_u);
+    return __fdiv_rn(__fmul_rn(-0.5f, t), nf);
+}
+
+__global__ void __launch_bounds__(EQ_ST_THREADS) k_divergence(const float *__restrict__ vx, const float *__restrict__ vy,
+                                                              float *__restrict__ div, float *__restrict__ p, EqLayout L) {
+    const int N = L.N, P = L.P;
+    const int i0 = 4 * (blockIdx.x * EQ_ST_THREADS + threadIdx.x);
+    const int jb = max(L.row0, 1) + blockIdx.y * EQ_ST_ROWS;           // owned interior rows
+    const int je = min(jb + EQ_ST_ROWS, min(L.row1, N - 1));
+    if (i0 > N - 2 || jb >= je) return;
+    const float nf = (float)N;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    size_t o = (size_t)i0 + (size_t)jb * P;
+    float4 up = ldg_f4(vy + o - P), mid = ldg_f4(vy + o);
+    for (int j = jb; j < je; ++j, o += P) {
+        const float4 dn = ldg_f4(vy + o + P);
+        const float4 c = ldg_f4(vx + o);
+        const float l = (i0 > 0) ? vx[o - 1] : 0.f;
+        const float r = vx[o + 4];                                     // column i0+4 <= P: inside the allocation
+        float4 d;
+        d.x = eq_div_cell(c.y, l, dn.x, up.x, nf);
+        d.y = eq_div_cell(c.z, c.x, dn.y, up.y, nf);
+        d.z = eq_div_cell(c.w, c.y, dn.z, up.z, nf);
+        d.w = eq_div_cell(r, c.z, dn.w, up.w, nf);
+        eq_store_group(div + o, i0, N, d);
+        eq_store_group(p + o, i0, N, zero);                            // :346
+        up = mid;
+        mid = dn;
+    }
 }
 
 // project, part 2 (fluid.rs:364-371): subtract the pressure gradient.
-__global__ void k_gradient(float *__restrict__ vx, float *__restrict__ vy,
-                           const float *__restrict__ p, EqLayout L) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int j = blockIdx.y + max(L.row0, 1);
-    if (i < 1 || i > L.N - 2) return;
-    const size_t o = (size_t)i + (size_t)j * L.P;
-    const float nf = (float)L.N;
-    vx[o] = __fsub_rn(vx[o], __fmul_rn(__fmul_rn(0.5f, __fsub_rn(p[o + 1], p[o - 1])), nf));
-    vy[o] = __fsub_rn(vy[o], __fmul_rn(__fmul_rn(0.5f, __fsub_rn(p[o + L.P], p[o - L.P])), nf));
+__device__ __forceinline__ float eq_grad_cell(float v, float p_hi, float p_lo, float nf) {
+    return __fsub_rn(v, __fmul_rn(__fmul_rn(0.5f, __fsub_rn(p_hi, p_lo)), nf));
+}
+
+__global__ void __launch_bounds__(EQ_ST_THREADS) k_gradient(float *__restrict__ vx, float *__restrict__ vy,
+                                                            const float *__restrict__ p, EqLayout L) {
+    const int N = L.N, P = L.P;
+    const int i0 = 4 * (blockIdx.x * EQ_ST_THREADS + threadIdx.x);
+    const int jb = max(L.row0, 1) + blockIdx.y * EQ_ST_ROWS;
+    const int je = min(jb + EQ_ST_ROWS, min(L.row1, N - 1));
+    if (i0 > N - 2 || jb >= je) return;
+    const float nf = (float)N;
+    size_t o = (size_t)i0 + (size_t)jb * P;
+    float4 up = ldg_f4(p + o - P), mid = ldg_f4(p + o);
+    for (int j = jb; j < je; ++j, o += P) {
+        const float4 dn = ldg_f4(p + o + P);
+        const float l = (i0 > 0) ? p[o - 1] : 0.f;
+        const float r = p[o + 4];
+        const float4 a = ldg_f4(vx + o), b = ldg_f4(vy + o);
+        float4 ax, by;
+        ax.x = eq_grad_cell(a.x, mid.y, l, nf);
+        ax.y = eq_grad_cell(a.y, mid.z, mid.x, nf);
+        ax.z = eq_grad_cell(a.z, mid.w, mid.y, nf);
+        ax.w = eq_grad_cell(a.w, r, mid.z, nf);
+        by.x = eq_grad_cell(b.x, dn.x, up.x, nf);
+        by.y = eq_grad_cell(b.y, dn.y, up.y, nf);
+        by.z = eq_grad_cell(b.z, dn.z, up.z, nf);
+        by.w = eq_grad_cell(b.w, dn.w, up.w, nf);
+        eq_store_group(vx + o, i0, N, ax);
+        eq_store_group(vy + o, i0, N, by);
+        up = mid;
+        mid = dn;
+    }
 }
 
 // ---------------------------------------------------------------------------
 // advect (fluid.rs:378-432).  One CTA per row because of the row-serial `break`
 // (quirk Q4): the first cell f of row j whose back-traced sample leaves the grid
 // copies its already-updated left neighbour and every cell after it keeps its
-// stale destination value.  The flag depends on the velocity at the cell only,
-// so: pass 1 = min-reduce f over the row, pass 2 = cells < f normal, cell f copy.
+// stale destination value.  The flag depends on the velocity at the cell only.
+//
+// Single pass: the CTA walks the row in segments of EQ_ADV_SEG consecutive columns, EQ_ADV_U
+// cells per thread (lane-interleaved, so velocity loads, the four bilinear gathers and the
+// stores of a warp are unit-stride).  Per segment: back-trace, one block-wide vote on the
+// flags, and only then the stores -- a segment without a flag (almost all of them) is written
+// in full, the first segment with one is written up to f and ends the row.  The velocities of
+// the next segment are requested before the vote, the EQ_ADV_U x 4 x NF gathers of a segment are
+// independent loads in flight together.
 // NF fields that share the velocity field (vx and vy self-advection,
 // fluid.rs:469-489) are advected by one launch.
 // ---------------------------------------------------------------------------
+#define EQ_ADV_THREADS 256
+#define EQ_ADV_U 4
+#define EQ_ADV_SEG (EQ_ADV_THREADS * EQ_ADV_U)
+
 struct AdvSample {
     float s0, s1, t0, t1;
     unsigned i0, i1, j0, j1;
@@ -236,10 +318,10 @@ __device__ __forceinline__ float eq_bilinear(const AdvSample &r, const EqPeerTab
 }
 
 template <int NF>
-__global__ void __launch_bounds__(256) k_advect(float *__restrict__ dA, const EqPeerTable d0A,
-                                                float *__restrict__ dB, const EqPeerTable d0B,
-                                                const float *__restrict__ vx, const float *__restrict__ vy,
-                                                float dt, EqLayout L) {
+__global__ void __launch_bounds__(EQ_ADV_THREADS) k_advect(float *__restrict__ dA, const EqPeerTable d0A,
+                                                           float *__restrict__ dB, const EqPeerTable d0B,
+                                                           const float *__restrict__ vx, const float *__restrict__ vy,
+                                                           float dt, EqLayout L) {
     const int N = L.N, P = L.P;
     const int j = blockIdx.x + max(L.row0, 1);              // owned interior rows
     const float nf = (float)N;
@@ -248,34 +330,65 @@ __global__ void __launch_bounds__(256) k_advect(float *__restrict__ dA, const Eq
     EQ_DYN_SMEM(adv_smem);
     int &s_first = *reinterpret_cast<int *>(adv_smem);
     if (threadIdx.x == 0) s_first = N;
-    __syncthreads();
-    int mine = N;
-    for (int i = 1 + threadIdx.x; i <= N - 2; i += blockDim.x) {
-        const AdvSample r = eq_backtrace(i, j, vx[row + i], vy[row + i], dtx, nf, N);
-        if (r.flagged) { mine = i; break; }                            // first one of this thread
+    float u[EQ_ADV_U], v[EQ_ADV_U];
+#pragma unroll
+    for (int q = 0; q < EQ_ADV_U; ++q) {
+        const int i = 1 + q * EQ_ADV_THREADS + (int)threadIdx.x;
+        u[q] = (i <= N - 2) ? vx[row + i] : 0.f;
+        v[q] = (i <= N - 2) ? vy[row + i] : 0.f;
     }
-    mine = min(mine, __shfl_xor_sync(0xffffffffu, mine, 16));
-    mine = min(mine, __shfl_xor_sync(0xffffffffu, mine, 8));
-    mine = min(mine, __shfl_xor_sync(0xffffffffu, mine, 4));
-    mine = min(mine, __shfl_xor_sync(0xffffffffu, mine, 2));
-    mine = min(mine, __shfl_xor_sync(0xffffffffu, mine, 1));
-    if ((threadIdx.x & 31) == 0 && mine < N) atomicMin(&s_first, mine);
-    __syncthreads();
-    const int f = s_first;                                             // N => no break in this row
-    const int last = min(f, N - 2);
-    for (int i = 1 + threadIdx.x; i <= last; i += blockDim.x) {
-        const int src = (i == f) ? i - 1 : i;                          // :421 copy of the updated left cell
-        float a, b = 0.f;
-        if (src == 0) {                                                // f == 1: the frame cell, untouched
-            a = dA[row];
-            if (NF == 2) b = dB[row];
-        } else {
-            const AdvSample r = eq_backtrace(src, j, vx[row + src], vy[row + src], dtx, nf, N);
-            a = eq_bilinear(r, d0A, P);
-            if (NF == 2) b = eq_bilinear(r, d0B, P);
+    for (int base = 1; base <= N - 2; base += EQ_ADV_SEG) {
+        AdvSample r[EQ_ADV_U];
+        int mine = N;
+#pragma unroll
+        for (int q = EQ_ADV_U - 1; q >= 0; --q) {
+            const int i = base + q * EQ_ADV_THREADS + (int)threadIdx.x;
+            r[q] = eq_backtrace(i, j, u[q], v[q], dtx, nf, N);
+            if (i <= N - 2 && r[q].flagged) mine = i;                  // descending q: the smallest flagged column
         }
-        dA[row + i] = a;
-        if (NF == 2) dB[row + i] = b;
+        // velocities of the next segment (in flight across the vote and the gathers)
+#pragma unroll
+        for (int q = 0; q < EQ_ADV_U; ++q) {
+            const int i = base + EQ_ADV_SEG + q * EQ_ADV_THREADS + (int)threadIdx.x;
+            u[q] = (i <= N - 2) ? vx[row + i] : 0.f;
+            v[q] = (i <= N - 2) ? vy[row + i] : 0.f;
+        }
+        const int any = __syncthreads_or(mine < N);                    // also orders the s_first initialisation
+        int f = N;
+        if (any) {
+            if (mine < N) atomicMin(&s_first, mine);
+            __syncthreads();
+            f = s_first;                                               // first flagged column of the row
+        }
+        const int last = min(f, N - 2);
+        float a[EQ_ADV_U], b[EQ_ADV_U];
+#pragma unroll
+        for (int q = 0; q < EQ_ADV_U; ++q) {
+            const int i = base + q * EQ_ADV_THREADS + (int)threadIdx.x;
+            a[q] = b[q] = 0.f;
+            if (i < f && i <= last) {
+                a[q] = eq_bilinear(r[q], d0A, P);
+                if (NF == 2) b[q] = eq_bilinear(r[q], d0B, P);
+            } else if (i == f && i <= last) {                          // :421 copy of the updated left cell
+                if (i == 1) {                                          // the frame cell, untouched
+                    a[q] = dA[row];
+                    if (NF == 2) b[q] = dB[row];
+                } else {
+                    const AdvSample rl = eq_backtrace(i - 1, j, vx[row + i - 1], vy[row + i - 1], dtx, nf, N);
+                    a[q] = eq_bilinear(rl, d0A, P);
+                    if (NF == 2) b[q] = eq_bilinear(rl, d0B, P);
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < EQ_ADV_U; ++q) {
+            const int i = base + q * EQ_ADV_THREADS + (int)threadIdx.x;
+            if (i <= last) {
+                dA[row + i] = a[q];
+                if (NF == 2) dB[row + i] = b[q];
+            }
+        }
+        if (any) break;                                                // :422 -- the rest of the row keeps its stale values
     }
 }
 

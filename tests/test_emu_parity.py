@@ -134,13 +134,18 @@ def test_red_black_close_to_oracle_red_black(oracle, emu_lib):
         assert P.bits_equal(got, x), P.describe_diff(got, x)
 
 
+@pytest.mark.parametrize("n", [200, 301])
 @pytest.mark.parametrize("orient", [P.ROW, P.COL, P.PASSIVE])
-def test_red_black_tiled_across_tiles(oracle, emu_lib, orient):
-    # 200 > one 128 x 64 tile in both directions; 5 iterations = one full pass of 4 plus a tail of 1
+def test_red_black_tiled_across_tiles(oracle, emu_lib, orient, n):
+    # k_rb_reg tiles write 232 x 40 cells: 200 spans several tile rows, 301 (odd: the last column pair is half
+    # outside the grid) also two tile columns, with rectangles across the tile seams; 5 iterations = one full
+    # pass of 4 plus a tail of 1
     rng = np.random.default_rng(1)
-    n, k = 200, 5
-    dev, ref = P.make_pair(oracle, emu_lib, n, k, [(60, 50, 140, 70), (120, 100, 131, 190), (1, 128, 40, 129)],
-                           mode="red_black")
+    k = 5
+    rects = [(60, 50, 140, 70), (120, 100, 131, 190), (1, 128, 40, 129)]
+    if n > 232:
+        rects += [(220, 30, 250, 50), (225, 200, 240, 299), (231, 90, 233, 92)]
+    dev, ref = P.make_pair(oracle, emu_lib, n, k, rects, mode="red_black")
     x, x0 = P.rnd(rng, n), P.rnd(rng, n)
     dev.upload("velocities_x", x)
     dev.upload("velocities_x0", x0)
