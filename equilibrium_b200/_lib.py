@@ -57,6 +57,14 @@ class EqProfile(C.Structure):
     ]
 
 
+class EqColors(C.Structure):
+    _fields_ = [("world", C.c_uint8 * 4), ("fluid", C.c_uint8 * 4), ("obstacle", C.c_uint8 * 4)]
+
+
+SNAP_DENSITY, SNAP_RGBA = 0, 1
+SNAPSHOT_SLOTS = 2
+
+
 class EquilibriumError(RuntimeError):
     def __init__(self, code: int, message: str):
         super().__init__(f"equilibrium_cuda error {code}: {message}")
@@ -93,6 +101,9 @@ SIGNATURES = {
     "eq_op_diffuse": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int64]),
     "eq_op_project": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64]),
     "eq_op_advect": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "eq_snapshot_begin": (C.c_int, [_H, C.c_int, C.c_int, C.POINTER(EqColors), C.c_void_p, C.c_size_t]),
+    "eq_snapshot_wait": (C.c_int, [_H, C.c_int]),
+    "eq_render_rgba": (C.c_int, [_H, C.POINTER(EqColors), C.c_void_p, C.c_size_t]),
     "eq_divergence_l2": (C.c_int, [_H, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "eq_set_stream": (C.c_int, [_H, C.c_void_p]),
     "eq_timer_start": (C.c_int, [_H]),

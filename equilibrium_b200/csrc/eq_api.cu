@@ -124,6 +124,11 @@ struct eq_fluid {
     unsigned *sync;                              // my cross-GPU sync slots
     unsigned halo_epoch, bar_epoch;
     bool attached;
+    // per-frame snapshots: staging slots, their events, the copy stream
+    cudaStream_t copy_stream;
+    void *snap_buf[EQ_SNAPSHOT_SLOTS];
+    cudaEvent_t snap_ready[EQ_SNAPSHOT_SLOTS], snap_done[EQ_SNAPSHOT_SLOTS];
+    bool snap_used[EQ_SNAPSHOT_SLOTS];
 };
 
 static size_t field_elems(const eq_fluid *h) { return (size_t)h->L.P * h->L.rows; }
@@ -677,10 +682,12 @@ static int advect(eq_fluid *h, int orientA, float *dA, const float *d0A, int ori
     {
         ProfScope ps(h, CAT_ADV, 1);
         const EqPeerTable tA = peer_table(h, d0A), tB = peer_table(h, d0B);
-        if (dB)
-            EQ_LAUNCH((k_advect<2>), owned_interior_rows(h), EQ_ADV_THREADS, 16, h->stream, dA, tA, dB, tB, vx, vy, h->prm.delta_t, L);
-        else
-            EQ_LAUNCH((k_advect<1>), owned_interior_rows(h), EQ_ADV_THREADS, 16, h->stream, dA, tA, nullptr, tB, vx, vy, h->prm.delta_t, L);
+        const int rows = owned_interior_rows(h);
+        const float dt = h->prm.delta_t;
+        if (dB && h->world > 1) EQ_LAUNCH((k_advect<2, true>), rows, EQ_ADV_THREADS, 16, h->stream, dA, tA, dB, tB, vx, vy, dt, L);
+        else if (dB) EQ_LAUNCH((k_advect<2, false>), rows, EQ_ADV_THREADS, 16, h->stream, dA, tA, dB, tB, vx, vy, dt, L);
+        else if (h->world > 1) EQ_LAUNCH((k_advect<1, true>), rows, EQ_ADV_THREADS, 16, h->stream, dA, tA, nullptr, tB, vx, vy, dt, L);
+        else EQ_LAUNCH((k_advect<1, false>), rows, EQ_ADV_THREADS, 16, h->stream, dA, tA, nullptr, tB, vx, vy, dt, L);
         TRY(check_launch("k_advect"));
     }
     TRY(barrier_all(h));     // ... and nobody may overwrite d0 while a neighbour still samples it
@@ -928,6 +935,15 @@ int eq_destroy(eq_fluid *h) {
     cudaFree(h->flags);
     cudaFree(h->sync);
     cudaFree(h->l2buf);
+    if (h->copy_stream) {
+        cudaStreamSynchronize(h->copy_stream);
+        cudaStreamDestroy(h->copy_stream);
+    }
+    for (int i = 0; i < EQ_SNAPSHOT_SLOTS; ++i) {
+        cudaFree(h->snap_buf[i]);
+        if (h->snap_ready[i]) cudaEventDestroy(h->snap_ready[i]);
+        if (h->snap_done[i]) cudaEventDestroy(h->snap_done[i]);
+    }
     if (h->job_tables) {
         for (auto &kv : *h->job_tables) cudaFree(kv.second);
         delete h->job_tables;
@@ -1280,6 +1296,62 @@ int eq_op_advect(eq_fluid *h, int orientation, int d_field, int d0_field, int vx
     TRY(f32_field(h, vy_field, &vy));
     if (!valid_orient(orientation) || d == d0 || d == vx || d == vy) return eq_fail(EQ_ERR_INVALID, "bad advect arguments");
     return advect(h, orientation, d, d0, 0, nullptr, nullptr, vx, vy);
+}
+
+// ---------------------------------------------------------------------------
+// per-frame snapshots and the colour map
+// ---------------------------------------------------------------------------
+static uint32_t pack_rgba(const uint8_t c[4]) {
+    return (uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[2] << 16) | ((uint32_t)c[3] << 24);
+}
+
+int eq_snapshot_begin(eq_fluid *h, int kind, int slot, const EqColors *colors, void *host_dst, size_t bytes) {
+    NEED(h);
+    if (slot < 0 || slot >= EQ_SNAPSHOT_SLOTS) return eq_fail(EQ_ERR_INVALID, "snapshot slot %d not in [0,%d)", slot, EQ_SNAPSHOT_SLOTS);
+    if (kind != EQ_SNAP_DENSITY && kind != EQ_SNAP_RGBA) return eq_fail(EQ_ERR_INVALID, "unknown snapshot kind %d", kind);
+    if (kind == EQ_SNAP_RGBA && !colors) return eq_fail(EQ_ERR_INVALID, "EQ_SNAP_RGBA needs colours");
+    const EqLayout L = h->L;
+    const size_t rows = (size_t)(L.row1 - L.row0), want = rows * L.N * 4;
+    if (!host_dst || bytes != want) return eq_fail(EQ_ERR_INVALID, "eq_snapshot_begin: expected %zu bytes (%zu owned rows), got %zu", want, rows, bytes);
+    if (!h->copy_stream) CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    if (!h->snap_buf[slot]) {
+        CU(cudaMalloc(&h->snap_buf[slot], want));
+        CU(cudaEventCreate(&h->snap_ready[slot]));
+        CU(cudaEventCreate(&h->snap_done[slot]));
+    }
+    // the staging slot may still be on its way to the host from its previous use
+    if (h->snap_used[slot]) CU(cudaStreamWaitEvent(h->stream, h->snap_done[slot], 0));
+    {
+        ProfScope ps(h, CAT_OTHER, kind == EQ_SNAP_RGBA ? 1 : 0);
+        if (kind == EQ_SNAP_DENSITY) {
+            CU(cudaMemcpy2DAsync(h->snap_buf[slot], (size_t)L.N * 4, h->f[EQ_F_DENSITY] + (size_t)L.row0 * L.P, (size_t)L.P * 4,
+                                 (size_t)L.N * 4, rows, cudaMemcpyDeviceToDevice, h->stream));
+        } else {
+            EQ_LAUNCH(k_render_rgba, row_grid(h, (int)rows), 256, 0, h->stream, h->f[EQ_F_DENSITY], h->cells,
+                      static_cast<uint32_t *>(h->snap_buf[slot]), pack_rgba(colors->world), pack_rgba(colors->fluid),
+                      pack_rgba(colors->obstacle), L);
+            TRY(check_launch("k_render_rgba"));
+        }
+    }
+    CU(cudaEventRecord(h->snap_ready[slot], h->stream));
+    CU(cudaStreamWaitEvent(h->copy_stream, h->snap_ready[slot], 0));
+    CU(cudaMemcpyAsync(host_dst, h->snap_buf[slot], want, cudaMemcpyDeviceToHost, h->copy_stream));
+    CU(cudaEventRecord(h->snap_done[slot], h->copy_stream));
+    h->snap_used[slot] = true;
+    return EQ_OK;
+}
+
+int eq_snapshot_wait(eq_fluid *h, int slot) {
+    NEED(h);
+    if (slot < 0 || slot >= EQ_SNAPSHOT_SLOTS) return eq_fail(EQ_ERR_INVALID, "snapshot slot %d not in [0,%d)", slot, EQ_SNAPSHOT_SLOTS);
+    if (!h->snap_used[slot]) return eq_fail(EQ_ERR_STATE, "no snapshot was started in slot %d", slot);
+    CU(cudaEventSynchronize(h->snap_done[slot]));
+    return EQ_OK;
+}
+
+int eq_render_rgba(eq_fluid *h, const EqColors *colors, void *host_rgba, size_t bytes) {
+    TRY(eq_snapshot_begin(h, EQ_SNAP_RGBA, 0, colors, host_rgba, bytes));
+    return eq_snapshot_wait(h, 0);
 }
 
 int eq_divergence_l2(eq_fluid *h, int vx_field, int vy_field, double *out) {

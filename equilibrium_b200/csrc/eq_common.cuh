@@ -138,6 +138,10 @@ __device__ __forceinline__ float4 lds_f32x4(uint32_t a) {
 __device__ __forceinline__ void cp_async_16s(uint32_t saddr, const void *gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(gmem) : "memory");
 }
+// 4-byte async copy global -> shared (through L1: read-only input of the kernel that issues it)
+__device__ __forceinline__ void cp_async_4s(uint32_t saddr, const void *gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(saddr), "l"(gmem) : "memory");
+}
 // pull a line into L2 ahead of time (no register, no shared memory)
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // mbarrier (shared::cta) -- each barrier gets a 16-byte slot (8 used on the device)

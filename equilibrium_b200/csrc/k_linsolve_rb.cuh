@@ -208,26 +208,39 @@ __global__ void __launch_bounds__(RBR_THREADS, 2) k_rb_reg(const float *__restri
     const bool colok0 = (gx >= 1 && gx <= N - 2), colok1 = (gx + 1 >= 1 && gx + 1 <= N - 2);
 
     float v[RBR_H][2];
-    // ---- stage: x into registers, x0 into my shared-memory slots ----
+    // ---- stage: x into registers, x0 into my shared-memory slots.  x0 goes global -> shared with cp.async (no
+    // register in between: the 249 registers of this kernel leave none to batch loads in), so all of a thread's
+    // 64 LDG.64 of x and 128 cp.async of x0 are in flight together.
+    const uint32_t x0s_u32 = smem_u32(x0s);
+    if (gx0 >= 0 && gx0 + RBR_W <= N && gy0 >= 0 && gy0 + RBR_H <= N) {   // the whole tile lies inside the grid
+        const size_t o0 = (size_t)gy0 * P + gx;
 #pragma unroll
-    for (int y = 0; y < RBR_H; ++y) {
-        const int gy = gy0 + y;
-        float2 xv = make_float2(0.f, 0.f), x0v = make_float2(0.f, 0.f);
-        if (gy >= 0 && gy < N) {
-            const size_t o = (size_t)gy * P + gx;                        // only dereferenced where in0 / in1
-            if (in0 && in1) {
-                xv = *reinterpret_cast<const float2 *>(xin + o);
-                x0v = *reinterpret_cast<const float2 *>(x0 + o);
-            } else {
-                if (in0) { xv.x = xin[o]; x0v.x = x0[o]; }
-                if (in1) { xv.y = xin[o + 1]; x0v.y = x0[o + 1]; }
-            }
+        for (int y = 0; y < RBR_H; ++y) {
+            const size_t o = o0 + (size_t)y * P;
+            cp_async_4s(x0s_u32 + 4u * ((0 * RBR_H + y) * RBR_THREADS + tid), x0 + o);
+            cp_async_4s(x0s_u32 + 4u * ((1 * RBR_H + y) * RBR_THREADS + tid), x0 + o + 1);
         }
-        v[y][0] = xv.x;
-        v[y][1] = xv.y;
-        x0s[(0 * RBR_H + y) * RBR_THREADS + tid] = x0v.x;
-        x0s[(1 * RBR_H + y) * RBR_THREADS + tid] = x0v.y;
+#pragma unroll
+        for (int y = 0; y < RBR_H; ++y) {
+            const float2 xv = *reinterpret_cast<const float2 *>(xin + o0 + (size_t)y * P);
+            v[y][0] = xv.x;
+            v[y][1] = xv.y;
+        }
+    } else {
+#pragma unroll
+        for (int y = 0; y < RBR_H; ++y) {
+            const int gy = gy0 + y;
+            const bool rowin = (gy >= 0 && gy < N);
+            const size_t o = (size_t)gy * P + gx;                        // only dereferenced where rowin && in0 / in1
+            v[y][0] = (rowin && in0) ? xin[o] : 0.f;
+            v[y][1] = (rowin && in1) ? xin[o + 1] : 0.f;
+            if (rowin && in0) cp_async_4s(x0s_u32 + 4u * ((0 * RBR_H + y) * RBR_THREADS + tid), x0 + o);
+            else x0s[(0 * RBR_H + y) * RBR_THREADS + tid] = 0.f;
+            if (rowin && in1) cp_async_4s(x0s_u32 + 4u * ((1 * RBR_H + y) * RBR_THREADS + tid), x0 + o + 1);
+            else x0s[(1 * RBR_H + y) * RBR_THREADS + tid] = 0.f;
+        }
     }
+    cp_async_commit();
     // ---- does set_boundaries have anything to do in this tile? ----
     bool need_fix;
     if (orient == EQ_PASSIVE) {
@@ -302,6 +315,7 @@ __global__ void __launch_bounds__(RBR_THREADS, 2) k_rb_reg(const float *__restri
         if (lane == 0) my_edge_l[y] = v[y][0];
         if (lane == 31) my_edge_r[y] = v[y][1];
     }
+    cp_async_wait<0>();                                                    // my x0 slots have landed (thread-private)
     __syncthreads();
 
     // one half-sweep: the cells of colour c.  Everything a cell reads has the other colour.

@@ -308,8 +308,10 @@ __device__ __forceinline__ AdvSample eq_backtrace(int i, int j, float u, float v
 
 // The back-trace may leave the slab: each sample row is read from the rank that owns it (direct
 // peer loads over NVLink; one rank => the local array).
+template <bool PEERS>
 __device__ __forceinline__ float eq_bilinear(const AdvSample &r, const EqPeerTable &t, int P) {
-    const float *lo = eq_owner_base(t, r.j0), *hi = eq_owner_base(t, r.j1);
+    // one rank: no owner look-up (it would index the parameter table dynamically and block the hoisting of the gathers)
+    const float *lo = PEERS ? eq_owner_base(t, r.j0) : t.base[0], *hi = PEERS ? eq_owner_base(t, r.j1) : t.base[0];
     const float a = lo[r.i0 + (size_t)r.j0 * P], b = hi[r.i0 + (size_t)r.j1 * P];
     const float c = lo[r.i1 + (size_t)r.j0 * P], d = hi[r.i1 + (size_t)r.j1 * P];
     const float l = __fadd_rn(__fmul_rn(r.t0, a), __fmul_rn(r.t1, b));
@@ -317,7 +319,7 @@ __device__ __forceinline__ float eq_bilinear(const AdvSample &r, const EqPeerTab
     return __fadd_rn(__fmul_rn(r.s0, l), __fmul_rn(r.s1, h));          // :424-428
 }
 
-template <int NF>
+template <int NF, bool PEERS>
 __global__ void __launch_bounds__(EQ_ADV_THREADS) k_advect(float *__restrict__ dA, const EqPeerTable d0A,
                                                            float *__restrict__ dB, const EqPeerTable d0B,
                                                            const float *__restrict__ vx, const float *__restrict__ vy,
@@ -360,35 +362,48 @@ __global__ void __launch_bounds__(EQ_ADV_THREADS) k_advect(float *__restrict__ d
             __syncthreads();
             f = s_first;                                               // first flagged column of the row
         }
-        const int last = min(f, N - 2);
-        float a[EQ_ADV_U], b[EQ_ADV_U];
+        if (!any) {
+            // the common case, branch-free: all EQ_ADV_U x 4 x NF gathers are issued before the first use (cells past
+            // column N-2 back-trace to valid clamped addresses; only their stores are predicated)
+            float a[EQ_ADV_U], b[EQ_ADV_U];
 #pragma unroll
-        for (int q = 0; q < EQ_ADV_U; ++q) {
-            const int i = base + q * EQ_ADV_THREADS + (int)threadIdx.x;
-            a[q] = b[q] = 0.f;
-            if (i < f && i <= last) {
-                a[q] = eq_bilinear(r[q], d0A, P);
-                if (NF == 2) b[q] = eq_bilinear(r[q], d0B, P);
-            } else if (i == f && i <= last) {                          // :421 copy of the updated left cell
-                if (i == 1) {                                          // the frame cell, untouched
-                    a[q] = dA[row];
-                    if (NF == 2) b[q] = dB[row];
-                } else {
-                    const AdvSample rl = eq_backtrace(i - 1, j, vx[row + i - 1], vy[row + i - 1], dtx, nf, N);
-                    a[q] = eq_bilinear(rl, d0A, P);
-                    if (NF == 2) b[q] = eq_bilinear(rl, d0B, P);
+            for (int q = 0; q < EQ_ADV_U; ++q) {
+                a[q] = eq_bilinear<PEERS>(r[q], d0A, P);
+                b[q] = (NF == 2) ? eq_bilinear<PEERS>(r[q], d0B, P) : 0.f;
+            }
+#pragma unroll
+            for (int q = 0; q < EQ_ADV_U; ++q) {
+                const int i = base + q * EQ_ADV_THREADS + (int)threadIdx.x;
+                if (i <= N - 2) {
+                    dA[row + i] = a[q];
+                    if (NF == 2) dB[row + i] = b[q];
                 }
             }
+            continue;
         }
+        // the segment that holds the first flagged column f of the row: cells before f as usual, cell f copies
+        // its already-updated left neighbour, the rest of the row keeps its stale values
+        const int last = min(f, N - 2);
 #pragma unroll
         for (int q = 0; q < EQ_ADV_U; ++q) {
             const int i = base + q * EQ_ADV_THREADS + (int)threadIdx.x;
-            if (i <= last) {
-                dA[row + i] = a[q];
-                if (NF == 2) dB[row + i] = b[q];
+            if (i > last) continue;
+            float a, b = 0.f;
+            if (i < f) {
+                a = eq_bilinear<PEERS>(r[q], d0A, P);
+                if (NF == 2) b = eq_bilinear<PEERS>(r[q], d0B, P);
+            } else if (i == 1) {                                       // :421, f == 1: the frame cell, untouched
+                a = dA[row];
+                if (NF == 2) b = dB[row];
+            } else {                                                   // :421 copy of the updated left cell
+                const AdvSample rl = eq_backtrace(i - 1, j, vx[row + i - 1], vy[row + i - 1], dtx, nf, N);
+                a = eq_bilinear<PEERS>(rl, d0A, P);
+                if (NF == 2) b = eq_bilinear<PEERS>(rl, d0B, P);
             }
+            dA[row + i] = a;
+            if (NF == 2) dB[row + i] = b;
         }
-        if (any) break;                                                // :422 -- the rest of the row keeps its stale values
+        break;                                                         // :422 -- the rest of the row keeps its stale values
     }
 }
 
@@ -443,4 +458,29 @@ __global__ void k_divergence_sq(const float *__restrict__ vx, const float *__res
     }
     for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
     if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(out, v);
+}
+
+// ---------------------------------------------------------------------------
+// density + cells_type -> RGBA, the pixel loop of RenderingListener::render_image
+// (renderer_helpers.rs:145-167): wall => obstacle colour; else density != 0 =>
+// [(density * fluid.r as f32) as u8, fluid.g, density as u8, 1]; else the world colour.
+// `as u8` saturates and maps NaN to 0.  Output is compact (pitch N), rows row0.. of the slab.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned eq_f32_as_u8(float v) { return min(__float2uint_rz(v), 255u); }
+
+__global__ void k_render_rgba(const float *__restrict__ density, const uint8_t *__restrict__ cells,
+                              uint32_t *__restrict__ out, uint32_t world, uint32_t fluid, uint32_t obstacle, EqLayout L) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y + L.row0;
+    if (i >= L.N) return;
+    const size_t o = (size_t)i + (size_t)j * L.P;
+    const float d = density[o];
+    uint32_t px = world;
+    if (cells[o]) {
+        px = obstacle;
+    } else if (d != 0.0f) {
+        const unsigned r = eq_f32_as_u8(__fmul_rn(d, (float)(fluid & 255u)));
+        px = r | (fluid & 0x0000ff00u) | (eq_f32_as_u8(d) << 16) | (1u << 24);
+    }
+    out[(size_t)i + (size_t)(j - L.row0) * L.N] = px;
 }

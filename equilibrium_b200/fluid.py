@@ -233,6 +233,39 @@ class Fluid:
         a = np.ascontiguousarray(arr, dtype=dt)
         _lib.check(self._lib, self._lib.eq_upload(self._h, fid, a.ctypes.data, a.nbytes))
 
+    # -- the caller's side of the frame loop (renderer_helpers.rs:61-65, 115-167) ----
+    OBSTACLES_COLOR = (255, 0, 0, 255)     # RenderingListener::default, renderer_helpers.rs:94-101 (Color32::RED)
+
+    def _colors(self, obstacles_color=None):
+        c = _lib.EqColors()
+        for dst, src in ((c.world, self.fluid_configs.world_color), (c.fluid, self.fluid_configs.fluid_color),
+                         (c.obstacle, obstacles_color or self.OBSTACLES_COLOR)):
+            for i in range(4):
+                dst[i] = int(src[i])
+        return c
+
+    def render_rgba(self, obstacles_color=None, out: np.ndarray | None = None) -> np.ndarray:
+        """render_image's pixel loop (renderer_helpers.rs:145-167) on the device: (owned rows, size, 4) u8."""
+        n = int(self.simulation_configs.size)
+        r0, r1 = self.owned_rows()
+        if out is None:
+            out = np.empty((r1 - r0, n, 4), dtype=np.uint8)
+        assert out.dtype == np.uint8 and out.nbytes == (r1 - r0) * n * 4 and out.flags["C_CONTIGUOUS"]
+        c = self._colors(obstacles_color)
+        _lib.check(self._lib, self._lib.eq_render_rgba(self._h, C.byref(c), out.ctypes.data, out.nbytes))
+        return out
+
+    def snapshot_begin(self, out: np.ndarray, slot: int = 0, rgba: bool = False, obstacles_color=None):
+        """Asynchronous frame snapshot (what `fluid.clone()` + send is for the reference's render thread,
+        renderer_helpers.rs:61-65): density (f32) or finished RGBA pixels into `out`, overlapping later steps.
+        `out` should live in pinned memory (eq_host_alloc) and must stay alive until snapshot_wait(slot)."""
+        c = self._colors(obstacles_color)
+        kind = _lib.SNAP_RGBA if rgba else _lib.SNAP_DENSITY
+        _lib.check(self._lib, self._lib.eq_snapshot_begin(self._h, kind, slot, C.byref(c), out.ctypes.data, out.nbytes))
+
+    def snapshot_wait(self, slot: int = 0):
+        _lib.check(self._lib, self._lib.eq_snapshot_wait(self._h, slot))
+
     density = property(lambda s: s.download("density"))
     velocities_x = property(lambda s: s.download("velocities_x"))
     velocities_y = property(lambda s: s.download("velocities_y"))

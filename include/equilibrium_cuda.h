@@ -171,6 +171,33 @@ int eq_op_project(eq_fluid *h, int vx_field, int vy_field, int p_field, int div_
 int eq_op_advect(eq_fluid *h, int orientation, int d_field, int d0_field, int vx_field,
                  int vy_field);                                                    /* fluid.rs:378-432 */
 
+/* ---- the caller's side of the frame loop -----------------------
+ * After every step() the reference deep-copies the whole Fluid and sends it to the render
+ * thread (`fluid.clone()` + mpsc, renderer_helpers.rs:61-65), which turns density + cells_type
+ * into RGBA pixels (render_image, renderer_helpers.rs:115-167) before the JPEG encode.  Here the
+ * frame leaves the GPU as ONE array -- f32 density or the finished RGBA pixels -- through a
+ * pinned-memory snapshot that overlaps the next step(). */
+typedef struct EqColors {      /* Color32 r,g,b,a of FluidConfigs::world_color / fluid_color  */
+    uint8_t world[4];          /* (configs.rs:37-48) and RenderingListener::obstacles_color   */
+    uint8_t fluid[4];          /* (renderer_helpers.rs:86-92)                                 */
+    uint8_t obstacle[4];
+} EqColors;
+typedef enum EqSnapshotKind {
+    EQ_SNAP_DENSITY = 0,       /* f32 density, row-major size*size (the rows this rank owns)  */
+    EQ_SNAP_RGBA = 1           /* 4 x u8 per cell, the pixel rule of renderer_helpers.rs:145-167 */
+} EqSnapshotKind;
+#define EQ_SNAPSHOT_SLOTS 2
+/* Enqueue a snapshot of the CURRENT state (stream-ordered after the steps issued so far): a
+ * device-side copy / colour-map into staging slot `slot`, then an asynchronous device->host copy
+ * on a second stream into `host_dst` (pinned memory from eq_host_alloc for real overlap;
+ * `bytes` = owned_rows * size * 4).  The call returns at once; later steps may run while the
+ * copy is in flight.  Re-using a slot waits (on the device) for its previous copy. */
+int eq_snapshot_begin(eq_fluid *h, int kind, int slot, const EqColors *colors, void *host_dst, size_t bytes);
+/* Block until the snapshot in `slot` has landed in its host buffer. */
+int eq_snapshot_wait(eq_fluid *h, int slot);
+/* Synchronous convenience: render_image's pixel loop for the owned rows into host memory. */
+int eq_render_rgba(eq_fluid *h, const EqColors *colors, void *host_rgba, size_t bytes);
+
 /* Diagnostics for BASELINE config 5: L2 norm of the velocity divergence
  * (same stencil as fluid.rs:341-345) over the owned interior. */
 int eq_divergence_l2(eq_fluid *h, int vx_field, int vy_field, double *out);

@@ -339,3 +339,32 @@ void *ref_fluid_field(ref_fluid *f, int id) {
     default: return NULL;
     }
 }
+
+/* Rust `f32 as u8`: truncates toward zero, saturates to 0..255, NaN -> 0. */
+static inline uint8_t f32_as_u8(float v) {
+    if (!(v > 0.0f)) return 0;          /* negatives, -0, NaN */
+    if (v >= 255.0f) return 255;
+    return (uint8_t)v;
+}
+
+/* renderer_helpers.rs:145-167 */
+void ref_render_rgba(const float *density, const uint8_t *cells, uint32_t size, uint32_t rows,
+                     const uint8_t world[4], const uint8_t fluid[4], const uint8_t obstacle[4],
+                     uint8_t *out) {
+    for (uint32_t y = 0; y < rows; ++y)
+        for (uint32_t x = 0; x < size; ++x) {
+            const size_t o = (size_t)x + (size_t)y * size;
+            const float d = density[o];
+            uint8_t *px = out + 4 * o;
+            if (cells[o]) {                                          /* :149-155 DefaultWall */
+                px[0] = obstacle[0]; px[1] = obstacle[1]; px[2] = obstacle[2]; px[3] = obstacle[3];
+            } else if (d != 0.0f) {                                  /* :156-162 */
+                px[0] = f32_as_u8(d * (float)fluid[0]);
+                px[1] = fluid[1];
+                px[2] = f32_as_u8(d);
+                px[3] = 1;
+            } else {                                                 /* :163-165 */
+                px[0] = world[0]; px[1] = world[1]; px[2] = world[2]; px[3] = world[3];
+            }
+        }
+}

@@ -98,6 +98,13 @@ void ref_lin_solve_red_black(int orientation, float *x, const float *x0, float a
                              uint32_t size, uint32_t rows, int64_t iters,
                              const uint8_t *cells);
 
+/* The pixel loop of RenderingListener::render_image (renderer_helpers.rs:145-167): one RGBA
+ * pixel per cell from density + cells_type.  colours = world, fluid, obstacle as r,g,b,a bytes
+ * (renderer_helpers.rs:122-143).  out = size*rows*4 bytes. */
+void ref_render_rgba(const float *density, const uint8_t *cells, uint32_t size, uint32_t rows,
+                     const uint8_t world[4], const uint8_t fluid[4], const uint8_t obstacle[4],
+                     uint8_t *out);
+
 #ifdef __cplusplus
 }
 #endif

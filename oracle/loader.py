@@ -60,6 +60,7 @@ def lib():
                               C.c_int64, u8p]
     L.ref_project.argtypes = [fp, fp, fp, fp, C.c_uint32, C.c_uint32, C.c_int64, u8p]
     L.ref_advect.argtypes = [C.c_int, fp, fp, fp, fp, C.c_uint32, C.c_uint32, C.c_float, u8p]
+    L.ref_render_rgba.argtypes = [fp, u8p, C.c_uint32, C.c_uint32, u8p, u8p, u8p, u8p]
     _lib = L
     return L
 
@@ -154,3 +155,13 @@ def advect(orientation, d, d0, vx, vy, delta_t, cells):
 
 def rect_valid(x0, y0, x1, y1, size) -> bool:
     return bool(lib().ref_rect_valid(x0, y0, x1, y1, size))
+
+
+def render_rgba(density, cells, world, fluid, obstacle) -> np.ndarray:
+    """renderer_helpers.rs:145-167: (rows, size, 4) u8 pixels."""
+    rows, size = density.shape
+    out = np.empty((rows, size, 4), dtype=np.uint8)
+    cols = [np.ascontiguousarray(np.array(c, dtype=np.uint8)) for c in (world, fluid, obstacle)]
+    lib().ref_render_rgba(_f(np.ascontiguousarray(density)), _u(np.ascontiguousarray(cells)), size, rows,
+                          _u(cols[0]), _u(cols[1]), _u(cols[2]), _u(out.reshape(-1)))
+    return out

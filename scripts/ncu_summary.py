@@ -21,7 +21,16 @@ for r in rows[2:]:
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 if len(rows) > 2:
-    hdr, data = rows[1], [r for r in rows[2:] if len(r) == len(rows[1])]
+    def _isint(v):
+        try:
+            int(v or 0)
+            return True
+        except ValueError:
+            return False
+    hdr = rows[1]
+    _c = hdr.index("Warp Stall Sampling (All Samples)")
+    # several kernels in one report: every kernel's table repeats the header rows -- keep data rows only
+    data = [r for r in rows[2:] if len(r) == len(hdr) and _isint(r[_c]) and r[0] != hdr[0]]
     idx = {h: i for i, h in enumerate(hdr)}
     stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
     tot = {s: sum(int(r[idx[s]] or 0) for r in data) for s in stalls}

@@ -161,6 +161,7 @@ static inline void sts_f32(uint32_t a, float v) { memcpy(eq_emu::dyn_smem() + a,
 static inline unsigned lds_u8(uint32_t a) { return eq_emu::dyn_smem()[a]; }
 static inline float4 lds_f32x4(uint32_t a) { float4 v; memcpy(&v, eq_emu::dyn_smem() + a, 16); return v; }
 static inline void cp_async_16s(uint32_t saddr, const void *gmem) { memcpy(eq_emu::dyn_smem() + saddr, gmem, 16); }
+static inline void cp_async_4s(uint32_t saddr, const void *gmem) { memcpy(eq_emu::dyn_smem() + saddr, gmem, 4); }
 static inline void sts_u32(uint32_t a, uint32_t v) { memcpy(eq_emu::dyn_smem() + a, &v, 4); }
 static inline uint32_t lds_u32(uint32_t a) { uint32_t v; memcpy(&v, eq_emu::dyn_smem() + a, 4); return v; }
 static inline void sts_release_cta_u32(uint32_t a, uint32_t v) { __atomic_store_n(reinterpret_cast<uint32_t *>(eq_emu::dyn_smem() + a), v, __ATOMIC_RELEASE); }
@@ -244,6 +245,7 @@ static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; 
 cudaError_t cudaEventCreate(cudaEvent_t *e);
 cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t);
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return cudaSuccess; }
 cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b);
 cudaError_t cudaEventDestroy(cudaEvent_t e);
 // "device memory" is POSIX shared memory so that another emulated rank (another process) can map

@@ -148,3 +148,47 @@ def check_steps(oracle, lib_path, n, k, frames_to_run, rects, *, with_impulses, 
         if every_frame or fr == frames_to_run - 1:
             assert_state_equal(dev, ref, f"N={n} K={k} frame {fr}")
     return dev, ref
+
+
+def check_render_and_snapshot(oracle, lib_path, n, rects, seed=0, steps=2):
+    """The caller's side of the frame loop: the device colour map against the
+    restatement of render_image's pixel loop (renderer_helpers.rs:145-167) on adversarial densities,
+    then double-buffered snapshots taken between steps against plain downloads."""
+    rng = np.random.default_rng(seed)
+    dev, ref = make_pair(oracle, lib_path, n, 2, rects)
+    d = (rng.standard_normal((n, n)) * 0.8).astype(np.float32)
+    flat = d.reshape(-1)
+    # zero / negative zero (world colour), saturation of `as u8` both ways, NaN (-> 0), infinities, denormals
+    special = np.array([0.0, -0.0, 1.0, 254.99, 255.0, 256.0, 1e9, -3.0, np.nan, np.inf, -np.inf, 1e-40,
+                        1.2259, 0.9999999, 1.0000001], dtype=np.float32)
+    pos = rng.choice(flat.size, size=special.size * 8, replace=False)
+    flat[pos] = np.tile(special, 8)
+    dev.upload("density", d)
+    world, fluid, obstacle = dev.fluid_configs.world_color, dev.fluid_configs.fluid_color, (255, 0, 0, 255)
+    want = oracle.render_rgba(d, ref.cells, world, fluid, obstacle)
+    got = dev.render_rgba(obstacle)
+    assert got.shape == (n, n, 4)
+    assert np.array_equal(got, want), f"render_rgba N={n}: {int((got != want).any(axis=2).sum())} pixels differ"
+    # snapshots: begin after each step, wait one step later (the copy overlaps the next step)
+    bufs = [np.empty((n, n), dtype=np.float32), np.empty((n, n, 4), dtype=np.uint8)]
+    dev.upload("density", np.nan_to_num(d, nan=0.5, posinf=2.0, neginf=-2.0))
+    expect = []
+    for s in range(steps):
+        dev.step()
+        rgba = bool(s & 1)
+        dev.snapshot_begin(bufs[s & 1], slot=s & 1, rgba=rgba, obstacles_color=obstacle)
+        dev.step()                                   # the state moves on while the snapshot is in flight
+        dev.snapshot_wait(s & 1)
+        expect.append((rgba, bufs[s & 1].copy()))
+    # replay on a second handle with plain downloads
+    dev2, _ = make_pair(oracle, lib_path, n, 2, rects)
+    dev2.upload("density", np.nan_to_num(d, nan=0.5, posinf=2.0, neginf=-2.0))
+    for s in range(steps):
+        dev2.step()
+        dens = dev2.download("density")
+        rgba, snap = expect[s]
+        if rgba:
+            assert np.array_equal(snap, oracle.render_rgba(dens, ref.cells, world, fluid, obstacle)), f"RGBA snapshot {s}"
+        else:
+            assert bits_equal(snap, dens), f"density snapshot {s}: {describe_diff(snap, dens)}"
+        dev2.step()

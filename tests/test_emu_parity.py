@@ -153,3 +153,8 @@ def test_red_black_tiled_across_tiles(oracle, emu_lib, orient, n):
     oracle.lin_solve(orient, x, x0, 0.37, 2.48, k, ref.cells, red_black=True)
     got = dev.download("velocities_x")
     assert P.bits_equal(got, x), P.describe_diff(got, x)
+
+
+@pytest.mark.parametrize("n", [64, 101])
+def test_render_rgba_and_snapshots(oracle, emu_lib, n):
+    P.check_render_and_snapshot(oracle, emu_lib, n, [(10, 10, 20, 30), (40, 5, 50, 60)])

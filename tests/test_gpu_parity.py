@@ -184,3 +184,8 @@ def test_config4_16384_lin_solve_direct(oracle, cuda_lib):
     # lin_solve with K=2 compared directly (about 10 s of oracle time)
     n = 16384
     P.check_lin_solve(oracle, cuda_lib, n, 2, P.random_rects(n, 16, 16384), P.COL)
+
+
+@pytest.mark.parametrize("n", [128, 1001])
+def test_render_rgba_and_snapshots(oracle, cuda_lib, n):
+    P.check_render_and_snapshot(oracle, cuda_lib, n, P.random_rects(n, 6, 3))

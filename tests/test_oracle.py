@@ -138,3 +138,19 @@ def test_symmetry_of_obstacle_free_scene(oracle):
     assert np.isfinite(f.vx).all() and np.isfinite(f.density).all()
     assert f.density.min() >= -1e-6 and f.density.max() <= 0.9 + 1e-6
     assert np.allclose(f.vx, f.vy.T, atol=5e-2)
+
+
+def test_render_rgba_known_answers(oracle):
+    """renderer_helpers.rs:145-167 with the default colours (configs.rs:56-57, Color32::RED obstacles):
+    wall -> obstacle colour; density != 0 -> [(density * 208) as u8, 88, density as u8, 1]; else world colour."""
+    d = np.array([[0.0, 0.9, 1.8, -1.0, 2.0, np.nan, -0.0, 0.9]], dtype=np.float32)
+    c = np.array([[0, 0, 0, 0, 0, 0, 0, 1]], dtype=np.uint8)
+    px = oracle.render_rgba(d, c, (94, 146, 162, 128), (208, 88, 157, 220), (255, 0, 0, 255))[0]
+    assert px[0].tolist() == [94, 146, 162, 128]          # density == 0: world colour
+    assert px[1].tolist() == [187, 88, 0, 1]               # 0.9 * 208 = 187.2 -> 187; 0.9 as u8 = 0
+    assert px[2].tolist() == [255, 88, 1, 1]               # 374.4 saturates; 1.8 as u8 = 1
+    assert px[3].tolist() == [0, 88, 0, 1]                 # negative saturates to 0, but density != 0
+    assert px[4].tolist() == [255, 88, 2, 1]
+    assert px[5].tolist() == [0, 88, 0, 1]                 # NaN != 0.0 is true; NaN as u8 = 0
+    assert px[6].tolist() == [94, 146, 162, 128]           # -0.0 == 0.0
+    assert px[7].tolist() == [255, 0, 0, 255]              # wall
