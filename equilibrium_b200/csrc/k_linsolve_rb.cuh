@@ -281,8 +281,15 @@ __global__ void __launch_bounds__(RBR_THREADS, 2) k_rb_reg(const float *__restri
                         if (e == 0) d0 = d; else d1 = d;
                     }
                 } else {
-                    const size_t o = (size_t)gy * P + gx;
-                    const unsigned c0 = in0 ? codes[o] : 0u, c1 = in1 ? codes[o + 1] : 0u;
+                    const size_t o = (size_t)gy * P + gx;                  // even: one 16-bit load fetches the pair
+                    unsigned c0 = 0u, c1 = 0u;
+                    if (in0 && in1) {
+                        const unsigned pair = *reinterpret_cast<const uint16_t *>(codes + o);
+                        c0 = pair & 255u;
+                        c1 = pair >> 8;
+                    } else if (in0) {
+                        c0 = codes[o];
+                    }
                     if (orient == EQ_ADJUST_ROW) {
                         d0 = c0 & 3u;                                     // 1 LEFT, 2 RIGHT
                         d1 = c1 & 3u;
@@ -297,7 +304,6 @@ __global__ void __launch_bounds__(RBR_THREADS, 2) k_rb_reg(const float *__restri
             cw[y >> 2] |= (d0 | (d1 << 4)) << (8 * (y & 3));
         }
     }
-    const bool negate = (orient != EQ_PASSIVE);                           // AdjustRow / AdjustColumn mirror with a sign flip
     // rows that are interior rows of the grid (uniform over the CTA)
     unsigned long long rowmask = 0ull;
 #pragma unroll
@@ -318,7 +324,9 @@ __global__ void __launch_bounds__(RBR_THREADS, 2) k_rb_reg(const float *__restri
     cp_async_wait<0>();                                                    // my x0 slots have landed (thread-private)
     __syncthreads();
 
-    // one half-sweep: the cells of colour c.  Everything a cell reads has the other colour.
+    // one half-sweep: the cells of colour c.  Everything a cell reads has the other colour, so the 62 updates of
+    // a thread are independent; the loop only LOADS from shared memory (x0 slots, the neighbour warps' edge
+    // columns) -- the edge columns of this colour are published after it, so that no store orders the rows.
     auto sweep = [&](auto colour_c, auto guard_c) {
         constexpr int C = decltype(colour_c)::value;
         constexpr bool GUARD = decltype(guard_c)::value;
@@ -344,8 +352,51 @@ __global__ void __launch_bounds__(RBR_THREADS, 2) k_rb_reg(const float *__restri
             } else {
                 v[y][e] = nv;
             }
-            if (e == 0) { if (lane == 0) my_edge_l[y] = v[y][0]; }
+        }
+#pragma unroll
+        for (int y = 1; y <= RBR_H - 2; ++y) {
+            if (((C ^ y) & 1) == 0) { if (lane == 0) my_edge_l[y] = v[y][0]; }
             else { if (lane == 31) my_edge_r[y] = v[y][1]; }
+        }
+    };
+
+    // set_boundaries (fluid.rs:252-272) on the registers.  Sources (wall cells; interior cells for Passive) are
+    // never destinations, so the order inside the pass does not matter.  Rows in which no lane of the warp holds
+    // a code are skipped with one vote.
+    auto fixup = [&](auto orient_c) {
+        constexpr int O = decltype(orient_c)::value;
+        const bool edge_l = (lane == 0 && !has_l), edge_r = (lane == 31 && !has_r);
+#pragma unroll
+        for (int y = 0; y < RBR_H; ++y) {
+            const unsigned byte = (cw[y >> 2] >> (8 * (y & 3))) & 0xffu;
+            if (!__any_sync(0xffffffffu, byte != 0u)) continue;
+            const unsigned d0 = byte & 15u, d1 = byte >> 4;
+            const float o0 = v[y][0], o1 = v[y][1];
+            float n0 = o0, n1 = o1;
+            if (O != EQ_ADJUST_COLUMN) {
+                float ln = __shfl_up_sync(0xffffffffu, o1, 1);            // left neighbour of my even cell
+                float rn = __shfl_down_sync(0xffffffffu, o0, 1);          // right neighbour of my odd cell
+                if (lane == 0 && has_l) ln = nb_edge_l[y];
+                if (lane == 31 && has_r) rn = nb_edge_r[y];
+                const float sl0 = (O == EQ_PASSIVE) ? ln : -ln, sr0 = (O == EQ_PASSIVE) ? o1 : -o1;
+                const float sl1 = (O == EQ_PASSIVE) ? o0 : -o0, sr1 = (O == EQ_PASSIVE) ? rn : -rn;
+                n0 = (d0 == RBR_DIR_LEFT && !edge_l) ? sl0 : ((d0 == RBR_DIR_RIGHT) ? sr0 : n0);
+                n1 = (d1 == RBR_DIR_LEFT) ? sl1 : ((d1 == RBR_DIR_RIGHT && !edge_r) ? sr1 : n1);
+            }
+            if (O != EQ_ADJUST_ROW) {
+                if (y > 0) {
+                    const float u0 = v[y - 1][0], u1 = v[y - 1][1];
+                    n0 = (d0 == RBR_DIR_UP) ? ((O == EQ_PASSIVE) ? u0 : -u0) : n0;
+                    n1 = (d1 == RBR_DIR_UP) ? ((O == EQ_PASSIVE) ? u1 : -u1) : n1;
+                }
+                if (y < RBR_H - 1) {
+                    const float b0 = v[y + 1][0], b1 = v[y + 1][1];
+                    n0 = (d0 == RBR_DIR_DOWN) ? ((O == EQ_PASSIVE) ? b0 : -b0) : n0;
+                    n1 = (d1 == RBR_DIR_DOWN) ? ((O == EQ_PASSIVE) ? b1 : -b1) : n1;
+                }
+            }
+            v[y][0] = n0;
+            v[y][1] = n1;
         }
     };
 
@@ -357,32 +408,9 @@ __global__ void __launch_bounds__(RBR_THREADS, 2) k_rb_reg(const float *__restri
         else sweep(std::integral_constant<int, 1>{}, std::false_type{});
         __syncthreads();
         if (need_fix) {
-            // ---- set_boundaries (fluid.rs:252-272) on the registers.  Sources (wall cells; interior cells for
-            // Passive) are never destinations, so the order inside the pass does not matter.
-#pragma unroll
-            for (int y = 0; y < RBR_H; ++y) {
-                float ln = __shfl_up_sync(0xffffffffu, v[y][1], 1);       // left neighbour of my even cell
-                float rn = __shfl_down_sync(0xffffffffu, v[y][0], 1);     // right neighbour of my odd cell
-                const unsigned byte = (cw[y >> 2] >> (8 * (y & 3))) & 0xffu;
-                if (byte) {
-                    if (lane == 0) ln = has_l ? nb_edge_l[y] : v[y][0];
-                    if (lane == 31) rn = has_r ? nb_edge_r[y] : v[y][1];
-                    const unsigned d0 = byte & 15u, d1 = byte >> 4;
-                    const float up0 = v[y > 0 ? y - 1 : y][0], dn0 = v[y < RBR_H - 1 ? y + 1 : y][0];
-                    const float up1 = v[y > 0 ? y - 1 : y][1], dn1 = v[y < RBR_H - 1 ? y + 1 : y][1];
-                    const bool edge_l = (lane == 0 && !has_l), edge_r = (lane == 31 && !has_r);
-                    if (d0) {
-                        const float s = (d0 == RBR_DIR_LEFT) ? ln : (d0 == RBR_DIR_RIGHT) ? v[y][1] : (d0 == RBR_DIR_UP) ? up0 : dn0;
-                        const bool valid = !((d0 == RBR_DIR_LEFT && edge_l) || (d0 == RBR_DIR_UP && y == 0) || (d0 == RBR_DIR_DOWN && y == RBR_H - 1));
-                        if (valid) v[y][0] = negate ? -s : s;
-                    }
-                    if (d1) {
-                        const float s = (d1 == RBR_DIR_LEFT) ? v[y][0] : (d1 == RBR_DIR_RIGHT) ? rn : (d1 == RBR_DIR_UP) ? up1 : dn1;
-                        const bool valid = !((d1 == RBR_DIR_RIGHT && edge_r) || (d1 == RBR_DIR_UP && y == 0) || (d1 == RBR_DIR_DOWN && y == RBR_H - 1));
-                        if (valid) v[y][1] = negate ? -s : s;
-                    }
-                }
-            }
+            if (orient == EQ_ADJUST_ROW) fixup(std::integral_constant<int, EQ_ADJUST_ROW>{});
+            else if (orient == EQ_ADJUST_COLUMN) fixup(std::integral_constant<int, EQ_ADJUST_COLUMN>{});
+            else fixup(std::integral_constant<int, EQ_PASSIVE>{});
             if (it + 1 < iters) {
 #pragma unroll
                 for (int y = 0; y < RBR_H; ++y) {

@@ -141,6 +141,8 @@ static inline int __all_sync(unsigned, int pred) {
     return all;
 }
 
+static inline int __any_sync(unsigned m, int pred) { return !__all_sync(m, !pred); }
+
 // ---- memory model stand-ins --------------------------------------------------
 static inline void __threadfence_system() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
