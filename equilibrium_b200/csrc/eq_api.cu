@@ -1314,10 +1314,12 @@ int eq_snapshot_begin(eq_fluid *h, int kind, int slot, const EqColors *colors, v
     const size_t rows = (size_t)(L.row1 - L.row0), want = rows * L.N * 4;
     if (!host_dst || bytes != want) return eq_fail(EQ_ERR_INVALID, "eq_snapshot_begin: expected %zu bytes (%zu owned rows), got %zu", want, rows, bytes);
     if (!h->copy_stream) CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-    if (!h->snap_buf[slot]) {
-        CU(cudaMalloc(&h->snap_buf[slot], want));
-        CU(cudaEventCreate(&h->snap_ready[slot]));
-        CU(cudaEventCreate(&h->snap_done[slot]));
+    if (!h->snap_buf[0]) {   // all slots at once: an allocation in the middle of a run would synchronise the device
+        for (int i = 0; i < EQ_SNAPSHOT_SLOTS; ++i) {
+            CU(cudaMalloc(&h->snap_buf[i], want));
+            CU(cudaEventCreate(&h->snap_ready[i]));
+            CU(cudaEventCreate(&h->snap_done[i]));
+        }
     }
     // the staging slot may still be on its way to the host from its previous use
     if (h->snap_used[slot]) CU(cudaStreamWaitEvent(h->stream, h->snap_done[slot], 0));

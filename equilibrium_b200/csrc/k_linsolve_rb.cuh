@@ -261,47 +261,42 @@ __global__ void __launch_bounds__(RBR_THREADS, 2) k_rb_reg(const float *__restri
 #pragma unroll
     for (int i = 0; i < RBR_H / 4; ++i) cw[i] = 0u;
     if (need_fix) {
+        // branch-free on purpose: every load below has a valid (clamped) address and is unconditional, so the 64
+        // loads of a thread are in flight together; the predicates only mask the results
+        const int gxc = in0 ? gx : 0;                                      // even, and column gxc + 1 <= P - 1 exists
+        if (orient == EQ_PASSIVE) {
+            // frame cells copy their interior neighbour (fluid.rs:182-186, conditional per quirk Q6)
+            const bool cf0 = in0 && col_fluid[gxc] != 0, cf1 = in1 && col_fluid[min(gxc + 1, N - 1)] != 0;
+            const bool fx0 = in0 && (gx == 0 || gx == N - 1), fx1 = in1 && (gx + 1 == 0 || gx + 1 == N - 1);
 #pragma unroll
-        for (int y = 0; y < RBR_H; ++y) {
-            const int gy = gy0 + y;
-            unsigned d0 = 0u, d1 = 0u;
-            if (gy >= 0 && gy < N) {
-                if (orient == EQ_PASSIVE) {
-                    // frame cells copy their interior neighbour (fluid.rs:182-186, conditional per quirk Q6)
-                    const bool fy = (gy == 0 || gy == N - 1);
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int cx = gx + e;
-                        unsigned d = 0u;
-                        if (cx >= 0 && cx < N) {
-                            const bool fx = (cx == 0 || cx == N - 1);
-                            if (fy && !fx) { if (col_fluid[cx]) d = (gy == 0) ? RBR_DIR_DOWN : RBR_DIR_UP; }
-                            else if (fx && !fy) { if (row_fluid[gy]) d = (cx == 0) ? RBR_DIR_RIGHT : RBR_DIR_LEFT; }
-                        }
-                        if (e == 0) d0 = d; else d1 = d;
-                    }
+            for (int y = 0; y < RBR_H; ++y) {
+                const int gy = gy0 + y, gyc = min(max(gy, 0), N - 1);
+                const bool rowin = (gy == gyc), fy = (gy == 0 || gy == N - 1);
+                const bool rf = row_fluid[gyc] != 0;
+                unsigned d0 = 0u, d1 = 0u;
+                if (fy) {
+                    d0 = (in0 && !fx0 && cf0) ? (gy == 0 ? RBR_DIR_DOWN : RBR_DIR_UP) : 0u;
+                    d1 = (in1 && !fx1 && cf1) ? (gy == 0 ? RBR_DIR_DOWN : RBR_DIR_UP) : 0u;
                 } else {
-                    const size_t o = (size_t)gy * P + gx;                  // even: one 16-bit load fetches the pair
-                    unsigned c0 = 0u, c1 = 0u;
-                    if (in0 && in1) {
-                        const unsigned pair = *reinterpret_cast<const uint16_t *>(codes + o);
-                        c0 = pair & 255u;
-                        c1 = pair >> 8;
-                    } else if (in0) {
-                        c0 = codes[o];
-                    }
-                    if (orient == EQ_ADJUST_ROW) {
-                        d0 = c0 & 3u;                                     // 1 LEFT, 2 RIGHT
-                        d1 = c1 & 3u;
-                    } else {
-                        d0 = (c0 >> 2) & 3u;                              // 1 UP, 2 DOWN
-                        d1 = (c1 >> 2) & 3u;
-                        d0 = d0 ? d0 + 2u : 0u;
-                        d1 = d1 ? d1 + 2u : 0u;
-                    }
+                    d0 = (fx0 && rf) ? (gx == 0 ? RBR_DIR_RIGHT : RBR_DIR_LEFT) : 0u;
+                    d1 = (fx1 && rf) ? (gx + 1 == 0 ? RBR_DIR_RIGHT : RBR_DIR_LEFT) : 0u;
                 }
+                if (!rowin) d0 = d1 = 0u;
+                cw[y >> 2] |= (d0 | (d1 << 4)) << (8 * (y & 3));
             }
-            cw[y >> 2] |= (d0 | (d1 << 4)) << (8 * (y & 3));
+        } else {
+            const unsigned shift = (orient == EQ_ADJUST_ROW) ? 0u : 2u;   // bits 0-1: 1 LEFT, 2 RIGHT; bits 2-3: 1 UP, 2 DOWN
+            const unsigned bump = (orient == EQ_ADJUST_ROW) ? 0u : 2u;    // direction numbers: LEFT 1, RIGHT 2, UP 3, DOWN 4
+#pragma unroll
+            for (int y = 0; y < RBR_H; ++y) {
+                const int gy = gy0 + y, gyc = min(max(gy, 0), N - 1);
+                const bool rowin = (gy == gyc);
+                const unsigned pair = *reinterpret_cast<const uint16_t *>(codes + (size_t)gyc * P + gxc);   // one 16-bit load
+                unsigned d0 = ((pair & 255u) >> shift) & 3u, d1 = ((pair >> 8) >> shift) & 3u;
+                d0 = (d0 && rowin && in0) ? d0 + bump : 0u;
+                d1 = (d1 && rowin && in1) ? d1 + bump : 0u;
+                cw[y >> 2] |= (d0 | (d1 << 4)) << (8 * (y & 3));
+            }
         }
     }
     // rows that are interior rows of the grid (uniform over the CTA)
@@ -369,13 +364,18 @@ __global__ void __launch_bounds__(RBR_THREADS, 2) k_rb_reg(const float *__restri
 #pragma unroll
         for (int y = 0; y < RBR_H; ++y) {
             const unsigned byte = (cw[y >> 2] >> (8 * (y & 3))) & 0xffu;
+            const float o0 = v[y][0], o1 = v[y][1];
+            float ln = 0.f, rn = 0.f;
+            if (O != EQ_ADJUST_COLUMN) {
+                // the shuffles stay outside the vote branch: the compiler cannot know the branch is warp-uniform and
+                // would route them through the WARPSYNC.COLLECTIVE slow path
+                ln = __shfl_up_sync(0xffffffffu, o1, 1);                  // left neighbour of my even cell
+                rn = __shfl_down_sync(0xffffffffu, o0, 1);                // right neighbour of my odd cell
+            }
             if (!__any_sync(0xffffffffu, byte != 0u)) continue;
             const unsigned d0 = byte & 15u, d1 = byte >> 4;
-            const float o0 = v[y][0], o1 = v[y][1];
             float n0 = o0, n1 = o1;
             if (O != EQ_ADJUST_COLUMN) {
-                float ln = __shfl_up_sync(0xffffffffu, o1, 1);            // left neighbour of my even cell
-                float rn = __shfl_down_sync(0xffffffffu, o0, 1);          // right neighbour of my odd cell
                 if (lane == 0 && has_l) ln = nb_edge_l[y];
                 if (lane == 31 && has_r) rn = nb_edge_r[y];
                 const float sl0 = (O == EQ_PASSIVE) ? ln : -ln, sr0 = (O == EQ_PASSIVE) ? o1 : -o1;

@@ -275,7 +275,8 @@ __global__ void __launch_bounds__(EQ_ST_THREADS) k_gradient(float *__restrict__ 
 
 struct AdvSample {
     float s0, s1, t0, t1;
-    unsigned i0, i1, j0, j1;
+    unsigned o00, o01, o10, o11;   // element offsets of (i0,j0) (i0,j1) (i1,j0) (i1,j1): 32 bits are enough up to 32768^2
+    unsigned j0, j1;               // sample rows (the owner look-up of the row-slab path)
     bool flagged;
 };
 
@@ -285,10 +286,11 @@ __device__ __forceinline__ float eq_clamp_rust(float v, float lo, float hi) {
     return v;
 }
 
-__device__ __forceinline__ AdvSample eq_backtrace(int i, int j, float u, float v, float dtx, float nf, int N) {
+// fi, fj = (float)i, (float)j (exact: the callers add small integers to one conversion per thread)
+__device__ __forceinline__ AdvSample eq_backtrace(float fi, float fj, float u, float v, float dtx, float nf, int N, int P) {
     AdvSample r;
-    float x = __fsub_rn((float)i, __fmul_rn(dtx, u));                  // :400
-    float y = __fsub_rn((float)j, __fmul_rn(dtx, v));                  // :401 (delta_t_y == delta_t_x)
+    float x = __fsub_rn(fi, __fmul_rn(dtx, u));                        // :400
+    float y = __fsub_rn(fj, __fmul_rn(dtx, v));                        // :401 (delta_t_y == delta_t_x)
     x = eq_clamp_rust(x, 0.5f, __fsub_rn(nf, 1.0f));                   // :403
     y = eq_clamp_rust(y, 0.5f, __fsub_rn(nf, 1.0f));                   // :404
     const float i0 = floorf(x), i1 = __fadd_rn(i0, 1.0f);              // :406-407
@@ -298,10 +300,15 @@ __device__ __forceinline__ AdvSample eq_backtrace(int i, int j, float u, float v
     r.t1 = __fsub_rn(y, j0);
     r.t0 = __fsub_rn(1.0f, r.t1);
     // `as u32` saturates and maps NaN to 0 (:417-418); idx! then clamps to N-1
-    r.i0 = min(__float2uint_rz(i0), (unsigned)(N - 1));
-    r.i1 = min(__float2uint_rz(i1), (unsigned)(N - 1));
+    const unsigned ui0 = min(__float2uint_rz(i0), (unsigned)(N - 1));
+    const unsigned ui1 = min(__float2uint_rz(i1), (unsigned)(N - 1));
     r.j0 = min(__float2uint_rz(j0), (unsigned)(N - 1));
     r.j1 = min(__float2uint_rz(j1), (unsigned)(N - 1));
+    const unsigned b0 = r.j0 * (unsigned)P, b1 = r.j1 * (unsigned)P;
+    r.o00 = b0 + ui0;
+    r.o01 = b1 + ui0;
+    r.o10 = b0 + ui1;
+    r.o11 = b1 + ui1;
     r.flagged = (i1 >= nf) || (j1 >= nf);                              // :420
     return r;
 }
@@ -312,8 +319,8 @@ template <bool PEERS>
 __device__ __forceinline__ float eq_bilinear(const AdvSample &r, const EqPeerTable &t, int P) {
     // one rank: no owner look-up (it would index the parameter table dynamically and block the hoisting of the gathers)
     const float *lo = PEERS ? eq_owner_base(t, r.j0) : t.base[0], *hi = PEERS ? eq_owner_base(t, r.j1) : t.base[0];
-    const float a = lo[r.i0 + (size_t)r.j0 * P], b = hi[r.i0 + (size_t)r.j1 * P];
-    const float c = lo[r.i1 + (size_t)r.j0 * P], d = hi[r.i1 + (size_t)r.j1 * P];
+    const float a = lo[r.o00], b = hi[r.o01];
+    const float c = lo[r.o10], d = hi[r.o11];
     const float l = __fadd_rn(__fmul_rn(r.t0, a), __fmul_rn(r.t1, b));
     const float h = __fadd_rn(__fmul_rn(r.t0, c), __fmul_rn(r.t1, d));
     return __fadd_rn(__fmul_rn(r.s0, l), __fmul_rn(r.s1, h));          // :424-428
@@ -328,6 +335,7 @@ __global__ void __launch_bounds__(EQ_ADV_THREADS) k_advect(float *__restrict__ d
     const int j = blockIdx.x + max(L.row0, 1);              // owned interior rows
     const float nf = (float)N;
     const float dtx = __fmul_rn(dt, (float)(N - 2));                   // :390
+    const float fj = (float)j;
     const size_t row = (size_t)j * P;
     EQ_DYN_SMEM(adv_smem);
     int &s_first = *reinterpret_cast<int *>(adv_smem);
@@ -342,10 +350,11 @@ __global__ void __launch_bounds__(EQ_ADV_THREADS) k_advect(float *__restrict__ d
     for (int base = 1; base <= N - 2; base += EQ_ADV_SEG) {
         AdvSample r[EQ_ADV_U];
         int mine = N;
+        const float fbase = (float)(base + (int)threadIdx.x);            // exact, as is fbase + q * 256 (< 2^24)
 #pragma unroll
         for (int q = EQ_ADV_U - 1; q >= 0; --q) {
             const int i = base + q * EQ_ADV_THREADS + (int)threadIdx.x;
-            r[q] = eq_backtrace(i, j, u[q], v[q], dtx, nf, N);
+            r[q] = eq_backtrace(__fadd_rn(fbase, (float)(q * EQ_ADV_THREADS)), fj, u[q], v[q], dtx, nf, N, P);
             if (i <= N - 2 && r[q].flagged) mine = i;                  // descending q: the smallest flagged column
         }
         // velocities of the next segment (in flight across the vote and the gathers)
@@ -396,7 +405,7 @@ __global__ void __launch_bounds__(EQ_ADV_THREADS) k_advect(float *__restrict__ d
                 a = dA[row];
                 if (NF == 2) b = dB[row];
             } else {                                                   // :421 copy of the updated left cell
-                const AdvSample rl = eq_backtrace(i - 1, j, vx[row + i - 1], vy[row + i - 1], dtx, nf, N);
+                const AdvSample rl = eq_backtrace((float)(i - 1), fj, vx[row + i - 1], vy[row + i - 1], dtx, nf, N, P);
                 a = eq_bilinear<PEERS>(rl, d0A, P);
                 if (NF == 2) b = eq_bilinear<PEERS>(rl, d0B, P);
             }
