@@ -28,17 +28,24 @@
 #define TBX_T 2                                   // iterations per job
 #endif
 #define TBX_LAG 2                                 // columns between consecutive sub-steps
+#ifndef TBX_SLOTS
+#define TBX_SLOTS 8                               // chunks in the staging ring (power of two)
+#endif
+#define TBX_RING (TBX_SLOTS * LSX_CW + 0u)        // columns in the ring = bytes per code row
+#define TBX_ROWB (TBX_RING * 4u)                  // bytes per tile row
+#define TBX_OMASK (TBX_ROWB - 4u)                 // byte-offset mask inside a row
+#define TBX_CMASK (TBX_RING - 1u)                 // column mask
 #define TBX_SK (2 * (TBX_T - 1))                  // rows the band has moved up at its last sub-step
 #define TBX_XROWS (34 + TBX_SK)                   // tile rows: global rows j0-SK-1 .. j0+32
 #define TBX_X0ROWS (32 + TBX_SK)                  // global rows j0-SK .. j0+31
 #define TBX_BACK ((32 + TBX_LAG * (TBX_T - 1) + 1 + LSX_CW - 1) / LSX_CW)   // after macro m, chunk m-BACK is final
 #define TBX_XS_OFF 0u
-#define TBX_X0_OFF (TBX_XROWS * 512u)
-#define TBX_CS_OFF (TBX_X0_OFF + TBX_X0ROWS * 512u)
-#define TBX_RAWIN_OFF (TBX_CS_OFF + TBX_XROWS * 128u)     // T rings: R of the row above, per sub-step
-#define TBX_RAWOUT_OFF (TBX_RAWIN_OFF + TBX_T * 512u)     // T rings: R of my last row, per sub-step
-#define TBX_BAR_OFF (TBX_RAWOUT_OFF + TBX_T * 512u)
-#define TBX_MISC_OFF (TBX_BAR_OFF + 3u * LSX_SLOTS * 16u)
+#define TBX_X0_OFF (TBX_XROWS * TBX_ROWB)
+#define TBX_CS_OFF (TBX_X0_OFF + TBX_X0ROWS * TBX_ROWB)
+#define TBX_RAWIN_OFF (TBX_CS_OFF + TBX_XROWS * TBX_RING)     // T rings: R of the row above, per sub-step
+#define TBX_RAWOUT_OFF (TBX_RAWIN_OFF + TBX_T * TBX_ROWB)     // T rings: R of my last row, per sub-step
+#define TBX_BAR_OFF (TBX_RAWOUT_OFF + TBX_T * TBX_ROWB)
+#define TBX_MISC_OFF (TBX_BAR_OFF + 3u * TBX_SLOTS * 16u)
 #define TBX_SMEM_BYTES (TBX_MISC_OFF + 16u)
 
 struct TbxProblem {
@@ -94,10 +101,10 @@ struct TbxJob {
         M = (N + 31 + TBX_LAG * (TBX_T - 1) + LSX_CW - 1) / LSX_CW;
         cflags = p.chunk_flags + (ORIENT == EQ_ADJUST_COLUMN ? (size_t)NBP * NC : 0) + (size_t)b * NC;
     }
-    __device__ __forceinline__ uint32_t bar_full(int q) const { return sbase + TBX_BAR_OFF + (uint32_t)(q % LSX_SLOTS) * 16u; }
-    __device__ __forceinline__ uint32_t bar_done(int q) const { return sbase + TBX_BAR_OFF + (uint32_t)(LSX_SLOTS + q % LSX_SLOTS) * 16u; }
-    __device__ __forceinline__ uint32_t bar_free(int q) const { return sbase + TBX_BAR_OFF + (uint32_t)(2 * LSX_SLOTS + q % LSX_SLOTS) * 16u; }
-    __device__ __forceinline__ uint32_t use_parity(int q) const { return (uint32_t)((q / LSX_SLOTS) & 1); }
+    __device__ __forceinline__ uint32_t bar_full(int q) const { return sbase + TBX_BAR_OFF + (uint32_t)(q % TBX_SLOTS) * 16u; }
+    __device__ __forceinline__ uint32_t bar_done(int q) const { return sbase + TBX_BAR_OFF + (uint32_t)(TBX_SLOTS + q % TBX_SLOTS) * 16u; }
+    __device__ __forceinline__ uint32_t bar_free(int q) const { return sbase + TBX_BAR_OFF + (uint32_t)(2 * TBX_SLOTS + q % TBX_SLOTS) * 16u; }
+    __device__ __forceinline__ uint32_t use_parity(int q) const { return (uint32_t)((q / TBX_SLOTS) & 1); }
     // tile row of a global row
     __device__ __forceinline__ int trow(int j) const { return j - (j0 - TBX_SK - 1); }
     // does any sub-step of this band touch the first or the last interior row (Passive frame-row copies)?
@@ -145,10 +152,10 @@ struct TbxJob {
         const int sub = lane % LPR, rr = lane / LPR;
         for (int q = 0; q < NC; ++q) {
             if (q + LSX_PF < NC) prefetch_l2(x0 + (size_t)(j0 + lane) * P + LSX_CW * (q + LSX_PF));
-            if (q >= LSX_SLOTS && !lsx_wait_bar(bar_free(q), use_parity(q - LSX_SLOTS), p.error, lane)) return false;
+            if (q >= TBX_SLOTS && !lsx_wait_bar(bar_free(q), use_parity(q - TBX_SLOTS), p.error, lane)) return false;
             TBX_TRACE(0, q);
             if (!lsx_wait_flags(flag_prev, (unsigned)q + 1u, false, flag_above, (unsigned)q + 1u, false, p.error, lane)) return false;
-            const uint32_t slot = (uint32_t)(q % LSX_SLOTS) * (LSX_CW * 4u);
+            const uint32_t slot = (uint32_t)(q % TBX_SLOTS) * (LSX_CW * 4u);
             const int col0 = LSX_CW * q;
             // x: global rows j0 .. j0+32 hold F_{k0-1} (band 0 also needs the frame row 0)
             const int jx_lo = (b == 0) ? 0 : j0;
@@ -156,7 +163,7 @@ struct TbxJob {
             for (int pass = 0; pass < (34 + RPP - 1) / RPP; ++pass) {
                 const int j = jx_lo + RPP * pass + rr;
                 if (j <= j0 + 32)
-                    cp_async_16s(sbase + TBX_XS_OFF + (uint32_t)trow(j) * 512u + slot + 16u * sub, x + (size_t)j * P + col0 + 4 * sub);
+                    cp_async_16s(sbase + TBX_XS_OFF + (uint32_t)trow(j) * TBX_ROWB + slot + 16u * sub, x + (size_t)j * P + col0 + 4 * sub);
             }
             if (b > 0) {
                 // edge rows: F_{k0+t-1} of global rows j0-2t, j0-2t+1 for sub-step t >= 1; raw tops for every sub-step
@@ -167,10 +174,10 @@ struct TbxJob {
                     if (id < 2 * (nsub - 1)) {
                         const int t = 1 + id / 2, which = id & 1;
                         const float *src = pr.edge + (((size_t)(t - 1) * NBP + b) * 2 + which) * P + col0 + 4 * sub;
-                        cp_async_16s(sbase + TBX_XS_OFF + (uint32_t)trow(j0 - 2 * t + which) * 512u + slot + 16u * sub, src);
+                        cp_async_16s(sbase + TBX_XS_OFF + (uint32_t)trow(j0 - 2 * t + which) * TBX_ROWB + slot + 16u * sub, src);
                     } else if (id >= 2 * (TBX_T - 1) && id - 2 * (TBX_T - 1) < nsub) {
                         const int t = id - 2 * (TBX_T - 1);
-                        cp_async_16s(sbase + TBX_RAWIN_OFF + (uint32_t)t * 512u + slot + 16u * sub,
+                        cp_async_16s(sbase + TBX_RAWIN_OFF + (uint32_t)t * TBX_ROWB + slot + 16u * sub,
                                      pr.raw + ((size_t)t * NBP + b) * P + col0 + 4 * sub);
                     }
                 }
@@ -180,11 +187,11 @@ struct TbxJob {
                 const int i = RPP * pass + rr;                   // x0 tile row i = global row j0-SK+i
                 const int j = j0 - TBX_SK + i;
                 if (i < TBX_X0ROWS && j >= 0)
-                    cp_async_16s(sbase + TBX_X0_OFF + (uint32_t)i * 512u + slot + 16u * sub, x0 + (size_t)j * P + col0 + 4 * sub);
+                    cp_async_16s(sbase + TBX_X0_OFF + (uint32_t)i * TBX_ROWB + slot + 16u * sub, x0 + (size_t)j * P + col0 + 4 * sub);
             }
             if (need_codes(q)) {
                 constexpr int CLPR = LSX_CW / 16;
-                const uint32_t cslot = (uint32_t)(q % LSX_SLOTS) * LSX_CW;
+                const uint32_t cslot = (uint32_t)(q % TBX_SLOTS) * LSX_CW;
                 if (ORIENT == EQ_PASSIVE) {
                     if (lane < CLPR) cp_async_16s(sbase + TBX_CS_OFF + cslot + 16u * lane, p.col_fluid + col0 + 16 * lane);
                 } else {
@@ -194,7 +201,7 @@ struct TbxJob {
                         const int t = (32 / CLPR) * pass + crr;  // code tile row t = global row j0-SK-1+t
                         const int j = j0 - TBX_SK - 1 + t;
                         if (t < TBX_XROWS - 1 && j >= 0)
-                            cp_async_16s(sbase + TBX_CS_OFF + (uint32_t)t * 128u + cslot + 16u * csub,
+                            cp_async_16s(sbase + TBX_CS_OFF + (uint32_t)t * TBX_RING + cslot + 16u * csub,
                                          p.codes + (size_t)j * P + col0 + 16 * csub);
                     }
                 }
@@ -215,7 +222,7 @@ struct TbxJob {
         for (int q = 0; q < NC; ++q) {
             if (!lsx_wait_bar(bar_done(q), use_parity(q), p.error, lane)) return false;
             TBX_TRACE(4, q);
-            const uint32_t slot = (uint32_t)(q % LSX_SLOTS) * (LSX_CW * 4u);
+            const uint32_t slot = (uint32_t)(q % TBX_SLOTS) * (LSX_CW * 4u);
             const int col0 = LSX_CW * q;
             // rows of the last sub-step (iteration k0+nsub-1); Passive also keeps the frame rows it touched
 #pragma unroll
@@ -224,7 +231,7 @@ struct TbxJob {
                 const bool interior = (j >= max(jf, 1) && j <= min(jf + 31, N - 2));
                 const bool frame = (ORIENT == EQ_PASSIVE) && ((j == 0 && jf <= 1) || (j == N - 1 && jf <= N - 2 && jf + 31 >= N - 2));
                 if (interior || frame) {
-                    const float4 v = lds_f32x4(sbase + TBX_XS_OFF + (uint32_t)trow(j) * 512u + slot + 16u * sub);
+                    const float4 v = lds_f32x4(sbase + TBX_XS_OFF + (uint32_t)trow(j) * TBX_ROWB + slot + 16u * sub);
                     *reinterpret_cast<float4 *>(x + (size_t)j * P + col0 + 4 * sub) = v;
                 }
             }
@@ -236,11 +243,11 @@ struct TbxJob {
                     const int id = RPP * pass + task;
                     if (id < 2 * (nsub - 1)) {
                         const int t = id / 2, which = id & 1;
-                        const float4 v = lds_f32x4(sbase + TBX_XS_OFF + (uint32_t)trow(j0 - 2 * t + 30 + which) * 512u + slot + 16u * sub);
+                        const float4 v = lds_f32x4(sbase + TBX_XS_OFF + (uint32_t)trow(j0 - 2 * t + 30 + which) * TBX_ROWB + slot + 16u * sub);
                         *reinterpret_cast<float4 *>(pr.edge + (((size_t)t * NBP + b + 1) * 2 + which) * P + col0 + 4 * sub) = v;
                     } else if (id >= 2 * (TBX_T - 1) && id - 2 * (TBX_T - 1) < nsub) {
                         const int t = id - 2 * (TBX_T - 1);
-                        const float4 v = lds_f32x4(sbase + TBX_RAWOUT_OFF + (uint32_t)t * 512u + slot + 16u * sub);
+                        const float4 v = lds_f32x4(sbase + TBX_RAWOUT_OFF + (uint32_t)t * TBX_ROWB + slot + 16u * sub);
                         *reinterpret_cast<float4 *>(pr.raw + ((size_t)t * NBP + b + 1) * P + col0 + 4 * sub) = v;
                     }
                 }
@@ -306,18 +313,18 @@ struct TbxJob {
             frame_bot[t] = (ORIENT == EQ_PASSIVE) && in_row[t] && row[t] == N - 2;
             const int tr = trow(row[t]);                          // may be out of the tile for inactive lanes of band 0
             const int trc = min(max(tr, 0), TBX_XROWS - 2);
-            xs_row[t] = xs0 + (uint32_t)trc * 512u;
+            xs_row[t] = xs0 + (uint32_t)trc * TBX_ROWB;
             // fast loops: where the lower neighbour is read (see frame_from_edge in the general loop)
-            down_row[t] = frame_from_edge[t] ? xs_row[t] : xs_row[t] + 512u;
-            x0_row[t] = sbase + TBX_X0_OFF + (uint32_t)min(max(tr - 1, 0), TBX_X0ROWS - 1) * 512u;
-            cs_row[t] = cs0 + (uint32_t)trc * 128u;
-            top_base[t] = (b == 0) ? xs0 + (uint32_t)trow(0) * 512u : sbase + TBX_RAWIN_OFF + (uint32_t)t * 512u;
+            down_row[t] = frame_from_edge[t] ? xs_row[t] : xs_row[t] + TBX_ROWB;
+            x0_row[t] = sbase + TBX_X0_OFF + (uint32_t)min(max(tr - 1, 0), TBX_X0ROWS - 1) * TBX_ROWB;
+            cs_row[t] = cs0 + (uint32_t)trc * TBX_RING;
+            top_base[t] = (b == 0) ? xs0 + (uint32_t)trow(0) * TBX_ROWB : sbase + TBX_RAWIN_OFF + (uint32_t)t * TBX_ROWB;
             cur[t] = prev2[t] = prev_up[t] = 0.f;
         }
         const uint32_t raw_out = sbase + TBX_RAWOUT_OFF;
 
         int m_cur = 0;
-        const uint32_t last_col = ((uint32_t)(N - 1) & 127u) << 2;
+        const uint32_t last_col = ((uint32_t)(N - 1) & TBX_CMASK) << 2;
         // ---- fast loop: straight-line code for the 16 steps x T sub-steps of a macro step in which nothing needs
         // a per-cell code lookup.  The operands of step s+1 are fetched before the arithmetic of step s (nobody
         // writes them later than step s-1), so the step-to-step chain of a sub-step is SHFL -> 3 FADD, FMUL, FADD,
@@ -339,12 +346,12 @@ struct TbxJob {
         auto fast_steps = [&](auto zone_c) {
             constexpr int ZONE = decltype(zone_c)::value;
             const int cb = LSX_CW * m_cur - lane;                 // column of sub-step 0 at the first step
-            const uint32_t ob = ((uint32_t)cb & 127u) << 2;
+            const uint32_t ob = ((uint32_t)cb & TBX_CMASK) << 2;
             float right[TBX_T], down[TBX_T], x0v[TBX_T], topv[TBX_T];
 #pragma unroll
             for (int t = 0; t < TBX_T; ++t) {
-                const uint32_t o = (ob - 4u * TBX_LAG * t) & 508u;
-                right[t] = lds_f32(xs_row[t] + ((o + 4u) & 508u));
+                const uint32_t o = (ob - 4u * TBX_LAG * t) & TBX_OMASK;
+                right[t] = lds_f32(xs_row[t] + ((o + 4u) & TBX_OMASK));
                 down[t] = lds_f32(down_row[t] + o);
                 x0v[t] = lds_f32(x0_row[t] + o);
                 topv[t] = first[t] ? lds_f32(top_base[t] + o) : 0.f;
@@ -362,8 +369,8 @@ struct TbxJob {
                 for (int t = 0; t < TBX_T; ++t) up[t] = __shfl_up_sync(0xffffffffu, cur[t], 1);
 #pragma unroll
                 for (int t = 0; t < TBX_T; ++t) {
-                    const uint32_t o = (ob + 4u * i - 4u * TBX_LAG * t) & 508u;
-                    const uint32_t o1 = (o + 4u) & 508u, o2 = (o + 8u) & 508u, om1 = (o - 4u) & 508u;
+                    const uint32_t o = (ob + 4u * i - 4u * TBX_LAG * t) & TBX_OMASK;
+                    const uint32_t o1 = (o + 4u) & TBX_OMASK, o2 = (o + 8u) & TBX_OMASK, om1 = (o - 4u) & TBX_OMASK;
                     right_n[t] = lds_f32(xs_row[t] + o2);
                     down_n[t] = lds_f32(down_row[t] + o1);
                     x0_n[t] = lds_f32(x0_row[t] + o1);
@@ -380,14 +387,14 @@ struct TbxJob {
                     }
                     // rows 1 and N-2 mirror the frame rows (which AdjustColumn never changes, quirk Q5):
                     // x[i,1] = -x[i,0] (the `up` this cell was computed with), x[i,N-2] = -x[i,N-1]
-                    if (ORIENT == EQ_ADJUST_COLUMN) below[t] = lds_f32(xs_row[t] + 512u + om1);
+                    if (ORIENT == EQ_ADJUST_COLUMN) below[t] = lds_f32(xs_row[t] + TBX_ROWB + om1);
                 }
                 // Phase B: arithmetic and the stores of the step
 #pragma unroll
                 for (int t = 0; t < TBX_T; ++t) {
                     const int c = cb + i - TBX_LAG * t;
-                    const uint32_t o = (ob + 4u * i - 4u * TBX_LAG * t) & 508u;
-                    const uint32_t om1 = (o - 4u) & 508u;
+                    const uint32_t o = (ob + 4u * i - 4u * TBX_LAG * t) & TBX_OMASK;
+                    const uint32_t om1 = (o - 4u) & TBX_OMASK;
                     float newv = gs_update(x0v[t], right[t], cur[t], down[t], up[t], a, c_recip);
                     bool interior = in_row[t], fin = in_row[t];
                     float F = cur[t];
@@ -405,10 +412,10 @@ struct TbxJob {
                         // fluid.rs:182-186 (every col_fluid is set here: passive_fast_frames)
                         if (ZONE == 1) { if (fin & rowfl[t] & (c == 2)) sts_f32(xs_row[t], cur[t]); }
                         if (ZONE == 2) { if (fin & rowfl[t] & (c == N - 1)) sts_f32(xs_row[t] + last_col, cur[t]); }
-                        if (fin & frame_top[t]) sts_f32(xs_row[t] - 512u + om1, cur[t]);
-                        if (fin & frame_bot[t]) sts_f32(xs_row[t] + 512u + om1, cur[t]);
+                        if (fin & frame_top[t]) sts_f32(xs_row[t] - TBX_ROWB + om1, cur[t]);
+                        if (fin & frame_bot[t]) sts_f32(xs_row[t] + TBX_ROWB + om1, cur[t]);
                     }
-                    if (interior & (lane == 31)) sts_f32(raw_out + (uint32_t)t * 512u + o, newv);
+                    if (interior & (lane == 31)) sts_f32(raw_out + (uint32_t)t * TBX_ROWB + o, newv);
                     prev2[t] = cur[t];
                     prev_up[t] = up[t];
                     cur[t] = newv;
@@ -436,11 +443,11 @@ struct TbxJob {
                     if (t < nsub) {
                         const int c = s - lane - TBX_LAG * t;       // column this lane computes now (0 = left frame cell)
                         const int cf = c - 1;                        // column finalised now
-                        const uint32_t o = ((uint32_t)c & 127u) << 2;
-                        const uint32_t om1 = (o - 4u) & 508u;
+                        const uint32_t o = ((uint32_t)c & TBX_CMASK) << 2;
+                        const uint32_t om1 = (o - 4u) & TBX_OMASK;
                         const float up = __shfl_up_sync(0xffffffffu, cur[t], 1);
-                        const float right = lds_f32(xs_row[t] + ((o + 4u) & 508u));
-                        float down = lds_f32(xs_row[t] + 512u + o);
+                        const float right = lds_f32(xs_row[t] + ((o + 4u) & TBX_OMASK));
+                        float down = lds_f32(xs_row[t] + TBX_ROWB + o);
                         const float x0v = lds_f32(x0_row[t] + o);
                         const float self = lds_f32(xs_row[t] + o);
                         const float top = first[t] ? lds_f32(top_base[t] + o) : up;
@@ -466,16 +473,16 @@ struct TbxJob {
                             // lane 31's lower neighbour is either the frame row N-1 (in the tile) or the first
                             // row of band b+1 at this sub-step, which patches the cell itself (below)
                             const bool below_is_frame = (row[t] == N - 2);
-                            const float below = (lane < 31) ? dn : lds_f32(xs_row[t] + 512u + om1);
+                            const float below = (lane < 31) ? dn : lds_f32(xs_row[t] + TBX_ROWB + om1);
                             const bool take_down = (code == EQ_CODE_COL_DOWN) & ((lane < 31) | below_is_frame);
                             F = (code == EQ_CODE_COL_UP) ? -prev_up[t] : (take_down ? -below : cur[t]);
                             // cell (c, j-1) above my first row belongs to band b-1 at this sub-step: it takes -R(c, j)
                             // when its code says DOWN.  For an intermediate iteration the cell lives on in MY tile
                             // (it is one of my edge rows); for the last one it is already in global x.
-                            const unsigned code0 = lds_u8(cs_row[t] - 128u + (o >> 2)) & 12u;
+                            const unsigned code0 = lds_u8(cs_row[t] - TBX_RING + (o >> 2)) & 12u;
                             const bool patch = gs_ok & (lane == 0) & (b > 0) & (code0 == EQ_CODE_COL_DOWN);
                             if (patch & (t == nsub - 1)) x[(size_t)(row[t] - 1) * P + c] = -newv;
-                            if (patch & (t != nsub - 1)) sts_f32(xs_row[t] - 512u + o, -newv);
+                            if (patch & (t != nsub - 1)) sts_f32(xs_row[t] - TBX_ROWB + o, -newv);
                         }
                         if (fin) sts_f32(xs_row[t] + om1, F);
                         if (ORIENT == EQ_PASSIVE) {
@@ -485,10 +492,10 @@ struct TbxJob {
                                 if (fin & rowfl[t] & (cf == N - 2)) sts_f32(xs_row[t] + last_col, cur[t]);
                             }
                             const bool colf = lds_u8(cs0 + (om1 >> 2)) != 0;
-                            if (fin & colf & (row[t] == 1)) sts_f32(xs_row[t] - 512u + om1, cur[t]);
-                            if (fin & colf & (row[t] == N - 2)) sts_f32(xs_row[t] + 512u + om1, cur[t]);
+                            if (fin & colf & (row[t] == 1)) sts_f32(xs_row[t] - TBX_ROWB + om1, cur[t]);
+                            if (fin & colf & (row[t] == N - 2)) sts_f32(xs_row[t] + TBX_ROWB + om1, cur[t]);
                         }
-                        if (gs_ok & (lane == 31)) sts_f32(raw_out + (uint32_t)t * 512u + o, newv);
+                        if (gs_ok & (lane == 31)) sts_f32(raw_out + (uint32_t)t * TBX_ROWB + o, newv);
                         prev2[t] = cur[t];
                         prev_up[t] = top;
                         cur[t] = newv;
@@ -518,8 +525,8 @@ struct TbxJob {
 #pragma unroll
                     for (int t = 0; t < TBX_T; ++t) {
                         if (t < nsub) {
-                            const uint32_t o = ((uint32_t)(s - lane - TBX_LAG * t) & 127u) << 2;
-                            const uint32_t o1 = (o + 4u) & 508u, om1 = (o - 4u) & 508u;
+                            const uint32_t o = ((uint32_t)(s - lane - TBX_LAG * t) & TBX_CMASK) << 2;
+                            const uint32_t o1 = (o + 4u) & TBX_OMASK, om1 = (o - 4u) & TBX_OMASK;
                             float up = __shfl_up_sync(0xffffffffu, cur[t], 1);
                             const float right = lds_f32(xs_row[t] + o1);
                             const float down = lds_f32(down_row[t] + o);
@@ -528,15 +535,15 @@ struct TbxJob {
                             const float newv = gs_update(x0v, right, cur[t], down, up, a, c_recip);
                             float F = cur[t];
                             if (ORIENT == EQ_ADJUST_COLUMN) {
-                                const float below = lds_f32(xs_row[t] + 512u + om1);
+                                const float below = lds_f32(xs_row[t] + TBX_ROWB + om1);
                                 F = col_top[t] ? -prev_up[t] : (col_bot[t] ? -below : F);
                             }
                             if (in_row[t]) sts_f32(xs_row[t] + om1, F);
                             if (ORIENT == EQ_PASSIVE) {
-                                if (frame_top[t]) sts_f32(xs_row[t] - 512u + om1, cur[t]);
-                                if (frame_bot[t]) sts_f32(xs_row[t] + 512u + om1, cur[t]);
+                                if (frame_top[t]) sts_f32(xs_row[t] - TBX_ROWB + om1, cur[t]);
+                                if (frame_bot[t]) sts_f32(xs_row[t] + TBX_ROWB + om1, cur[t]);
                             }
-                            if (lane == 31) sts_f32(raw_out + (uint32_t)t * 512u + o, newv);
+                            if (lane == 31) sts_f32(raw_out + (uint32_t)t * TBX_ROWB + o, newv);
                             prev2[t] = cur[t];
                             prev_up[t] = up;
                             cur[t] = newv;
@@ -574,10 +581,10 @@ __global__ void __launch_bounds__(LSX_THREADS, 5) k_linsolve_tb(const TbxParams 
             const unsigned t = (ld_volatile_s32(p.error) != 0) ? 0xffffffffu : atomicAdd(p.ticket, 1u);
             sts_u32(sbase + TBX_MISC_OFF, t);
             sts_u32(sbase + TBX_MISC_OFF + 4u, 0u);
-            for (int i = 0; i < LSX_SLOTS; ++i) {
+            for (int i = 0; i < TBX_SLOTS; ++i) {
                 mbar_init(sbase + TBX_BAR_OFF + (uint32_t)i * 16u, 32u);
-                mbar_init(sbase + TBX_BAR_OFF + (uint32_t)(LSX_SLOTS + i) * 16u, 1u);
-                mbar_init(sbase + TBX_BAR_OFF + (uint32_t)(2 * LSX_SLOTS + i) * 16u, 1u);
+                mbar_init(sbase + TBX_BAR_OFF + (uint32_t)(TBX_SLOTS + i) * 16u, 1u);
+                mbar_init(sbase + TBX_BAR_OFF + (uint32_t)(2 * TBX_SLOTS + i) * 16u, 1u);
             }
         }
         __syncthreads();
