@@ -299,11 +299,9 @@ __global__ void __launch_bounds__(RBR_THREADS, 2) k_rb_reg(const float *__restri
             }
         }
     }
-    // rows that are interior rows of the grid (uniform over the CTA)
-    unsigned long long rowmask = 0ull;
-#pragma unroll
-    for (int y = 0; y < RBR_H; ++y)
-        if (gy0 + y >= 1 && gy0 + y <= N - 2) rowmask |= 1ull << y;
+    // interior rows of the grid inside this tile: y in [ylo, yhi] (uniform over the CTA; compared against the
+    // unrolled row index, so the guarded sweep needs no precomputed per-row predicate)
+    const int ylo = max(1 - gy0, 1), yhi = min(N - 2 - gy0, RBR_H - 2);
     const bool guard = !(gx0 >= 1 && gx0 + RBR_W - 1 <= N - 2 && gy0 >= 1 && gy0 + RBR_H - 1 <= N - 2);
     float *my_edge_l = edge + (w * 2 + 0) * RBR_H;                         // lane 0 publishes its even column here
     float *my_edge_r = edge + (w * 2 + 1) * RBR_H;                         // lane 31 its odd column
@@ -311,10 +309,13 @@ __global__ void __launch_bounds__(RBR_THREADS, 2) k_rb_reg(const float *__restri
     const float *nb_edge_r = edge + (min(w + 1, RBR_WARPS - 1) * 2 + 0) * RBR_H;   // left edge of the warp to my right
     const bool has_l = (w > 0), has_r = (w < RBR_WARPS - 1);
 
+    // lanes 0 and 31 publish their outer column: one predicated store per row (two separate `if`s compile to branches)
+    float *const my_edge = (lane == 0) ? my_edge_l : my_edge_r;
+    const bool is_edge_lane = (lane == 0 || lane == 31);
 #pragma unroll
     for (int y = 0; y < RBR_H; ++y) {
-        if (lane == 0) my_edge_l[y] = v[y][0];
-        if (lane == 31) my_edge_r[y] = v[y][1];
+        const float ev = (lane == 0) ? v[y][0] : v[y][1];
+        if (is_edge_lane) my_edge[y] = ev;
     }
     cp_async_wait<0>();                                                    // my x0 slots have landed (thread-private)
     __syncthreads();
@@ -342,7 +343,7 @@ __global__ void __launch_bounds__(RBR_THREADS, 2) k_rb_reg(const float *__restri
             }
             const float nv = gs_update(x0s[(e * RBR_H + y) * RBR_THREADS + tid], right, left, v[y + 1][e], v[y - 1][e], a, c_recip);
             if (GUARD) {
-                const bool ok = (e == 0 ? colok0 : colok1) && ((rowmask >> y) & 1ull);
+                const bool ok = (e == 0 ? colok0 : colok1) && y >= ylo && y <= yhi;
                 v[y][e] = ok ? nv : v[y][e];
             } else {
                 v[y][e] = nv;
@@ -414,8 +415,8 @@ __global__ void __launch_bounds__(RBR_THREADS, 2) k_rb_reg(const float *__restri
             if (it + 1 < iters) {
 #pragma unroll
                 for (int y = 0; y < RBR_H; ++y) {
-                    if (lane == 0) my_edge_l[y] = v[y][0];
-                    if (lane == 31) my_edge_r[y] = v[y][1];
+                    const float ev = (lane == 0) ? v[y][0] : v[y][1];
+                    if (is_edge_lane) my_edge[y] = ev;
                 }
             }
             __syncthreads();
