@@ -391,9 +391,36 @@ def main():
         # ---- red-black fast path on the same workload (same slabs when world > 1) --------
         g = build_fluid(wl, "red_black", device=local_rank, rank=rank, world=world)
         ms_rb = time_device_resident(g, n, steps, warmup, seed=0, world=world)
+        g.profile_reset()
+        g.profile_enable(True)
+        g.step_n(steps)
+        prb = g.profile()
+        g.profile_enable(False)
+        rank_barrier(world)
+        # one k_rb_reg launch = RB_T (4) iterations of one field; lin_solve_launches also counts a corner kernel per field
+        rb_iters = 4
+        rb_launches = max(1, 5 * prb["steps"] * ((k + rb_iters - 1) // rb_iters))
+        rb_bytes = 12.0 * prb["lin_solve_cell_iters"]
+        rb_s = prb["lin_solve_ms"] * 1e-3
+        rb_traffic = None
+        if os.path.exists(tp) and world == 1:
+            with open(tp) as fh:
+                rec = json.load(fh).get(args.workload) or {}
+            rb_traffic = rec.get("rb_dram_bytes_per_launch")
         line["red_black"] = {"value": n * n * steps / (ms_rb * 1e-3), "unit": UNIT, "ms_per_step": ms_rb / steps,
                              "n_gpus": world,
-                             "note": "same K, red-black ordering; tolerance-checked, not bit-exact"}
+                             "note": "same K, red-black ordering; bit-identical to the oracle's red-black restatement, "
+                                     "tolerance-checked against the reference's order (tests/test_red_black.py)",
+                             "phases_ms_per_step": {x: prb[x] / max(1, prb["steps"]) for x in
+                                                    ["lin_solve_ms", "advect_ms", "project_ms", "boundary_ms", "other_ms"]},
+                             "roofline": {"bound": "hbm", "kernel": "k_rb_reg (tile in registers, 4 iterations per launch)",
+                                          "achieved": rb_bytes / rb_s / 1e9 if rb_s > 0 else 0.0, "peak": peak, "unit": "GB/s",
+                                          "frac": (rb_bytes / rb_s / 1e9 / peak) if rb_s > 0 else 0.0,
+                                          "traffic": rb_traffic, "per": "GPU (rank 0)" if world > 1 else "GPU",
+                                          "algorithmic_bytes_per_launch": rb_bytes / rb_launches,
+                                          "launch_ms": prb["lin_solve_ms"] / rb_launches,
+                                          "physical_frac": (rb_traffic / (prb["lin_solve_ms"] / rb_launches * 1e-3) / 1e9 / peak)
+                                                           if rb_traffic and rb_s > 0 else None}}
         g.close()
     if not args.no_extras and world == 1:
         # ---- CPU baseline beside it -----------------------------------------------------
