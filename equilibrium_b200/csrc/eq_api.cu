@@ -586,6 +586,20 @@ static int lin_solve_exact_tb(eq_fluid *h, const LinSolveReq *req, int nreq, int
     return EQ_OK;
 }
 
+// rank r's copy of one of my float arrays (a field or the red-black ping-pong buffer); nullptr outside [0, world)
+static int peer_buffer(eq_fluid *h, const float *mine, int r, float **out) {
+    *out = nullptr;
+    if (r < 0 || r >= h->world) return EQ_OK;
+    if (mine == h->rb_tmp) {
+        *out = h->peer_tmp[r];
+        return EQ_OK;
+    }
+    const int fi = field_index(h, mine);
+    if (fi < 0) return eq_fail(EQ_ERR_INVALID, "peer look-up of an unknown array");
+    *out = h->peer_f[r][fi];
+    return EQ_OK;
+}
+
 static int lin_solve_red_black(eq_fluid *h, const LinSolveReq *req, int nreq, int64_t iters) {
     const EqLayout L = h->L;
     const int rows = L.row1 - L.row0;
@@ -600,18 +614,27 @@ static int lin_solve_red_black(eq_fluid *h, const LinSolveReq *req, int nreq, in
         float *cur = req[i].x, *other = h->rb_tmp;
         // tiles at a slab edge recompute RB_H rows of the neighbour: they need its x0 there
         TRY(halo_xchg(h, const_cast<float *>(req[i].x0), RB_H));
+        bool pushed = false;     // the previous k_rb_reg launch wrote my boundary rows into the neighbours' ghost rows
         for (int64_t done = 0; done < iters; done += RB_T) {
             const int it = (int)std::min<int64_t>(RB_T, iters - done);
-            TRY(halo_xchg(h, cur, RB_H));
+            // ghost rows of `cur`: copied by the exchange kernel before the first launch, pushed by k_rb_reg itself
+            // afterwards (then the exchange is only the neighbour barrier: nrows = 0)
+            TRY(halo_xchg(h, cur, pushed ? 0 : RB_H));
             if (use_tiled) {
                 EQ_LAUNCH(k_rb_tiled, grid_t, RB_THREADS, RB_SMEM_BYTES, h->stream, cur, other, req[i].x0, h->codes,
                           h->row_fluid, h->col_fluid, req[i].a, c_recip, req[i].orient, it, L.row0, L.row1, L);
                 TRY(check_launch("k_rb_tiled"));
             } else {
+                float *pu = nullptr, *pd = nullptr;
+                if (h->world > 1) {
+                    TRY(peer_buffer(h, other, h->rank - 1, &pu));
+                    TRY(peer_buffer(h, other, h->rank + 1, &pd));
+                }
                 EQ_LAUNCH(k_rb_reg, grid_r, RBR_THREADS, RBR_SMEM_BYTES, h->stream, cur, other, req[i].x0, h->codes,
                           h->chunk_flags, h->row_fluid, h->col_fluid, req[i].a, c_recip, req[i].orient, it, L.row0, L.row1,
-                          ty0, L);
+                          ty0, pu, pd, L);
                 TRY(check_launch("k_rb_reg"));
+                pushed = (h->world > 1);
             }
             std::swap(cur, other);
         }

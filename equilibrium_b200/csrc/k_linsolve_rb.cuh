@@ -195,6 +195,7 @@ __global__ void __launch_bounds__(RBR_THREADS, 2) k_rb_reg(const float *__restri
                                                            const uint8_t *__restrict__ row_fluid,
                                                            const uint8_t *__restrict__ col_fluid, float a, float c_recip,
                                                            int orient, int iters, int row_lo, int row_hi, int tile_y0,
+                                                           float *__restrict__ peer_up_out, float *__restrict__ peer_down_out,
                                                            EqLayout L) {
     EQ_DYN_SMEM(rbr_smem);
     float *x0s = reinterpret_cast<float *>(rbr_smem);                    // [2][RBR_H][RBR_THREADS], thread-private slots
@@ -431,6 +432,14 @@ __global__ void __launch_bounds__(RBR_THREADS, 2) k_rb_reg(const float *__restri
                 const size_t o = (size_t)gy * P + gx;
                 if (in1) *reinterpret_cast<float2 *>(xout + o) = make_float2(v[y][0], v[y][1]);
                 else xout[o] = v[y][0];
+                // row slabs: my first / last RBR_HALO rows are the neighbours' ghost rows for the next launch --
+                // written straight into their copy of xout over NVLink (no separate copy kernel, only a barrier)
+                float *peer = (peer_up_out && gy < row_lo + RBR_HALO) ? peer_up_out
+                            : ((peer_down_out && gy >= row_hi - RBR_HALO) ? peer_down_out : nullptr);
+                if (peer) {
+                    if (in1) *reinterpret_cast<float2 *>(peer + o) = make_float2(v[y][0], v[y][1]);
+                    else peer[o] = v[y][0];
+                }
             }
         }
     }

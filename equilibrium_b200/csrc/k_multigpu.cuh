@@ -56,7 +56,8 @@ __global__ void __launch_bounds__(1024) k_halo_exchange(EqHaloArgs a, EqLayout L
         ok = eq_xgpu_wait(mine + 0, a.epoch, a.error) ? 1 : 0;
     }
     __syncthreads();
-    if (!ok) return;
+    if (!ok || a.nrows <= 0) return;                       // nrows == 0: neighbour barrier only (the producer kernel
+                                                           // pushed its boundary rows itself, see k_rb_reg)
     const int row = dir == 0 ? L.row0 : L.row1 - a.nrows;  // first / last owned rows
     const float4 *src = reinterpret_cast<const float4 *>(a.field + (size_t)row * L.P);
     float4 *dst = reinterpret_cast<float4 *>(peer + (size_t)row * L.P);

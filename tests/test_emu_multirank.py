@@ -108,9 +108,10 @@ def test_lin_solve_across_two_slabs(oracle, emu_lib, orient):
     assert P.bits_equal(got, x), P.describe_diff(got, x)
 
 
-@pytest.mark.parametrize("n,k", [(96, 3), (200, 6)])
-def test_red_black_across_slabs_matches_its_restatement(oracle, emu_lib, n, k):
-    world = 2
+@pytest.mark.parametrize("world,n,k", [(2, 96, 3), (2, 200, 6), (3, 200, 9)])
+def test_red_black_across_slabs_matches_its_restatement(oracle, emu_lib, world, n, k):
+    # k > 4: the launches after the first read ghost rows that the neighbours' k_rb_reg pushed itself (3 ranks: the
+    # middle one pushes both ways)
     rects = [(10, 40, 60, 70)]
     fluids = make_rank_fluids(emu_lib, world, n, k, rects, mode="red_black")
     ref = oracle.RefFluid(n, 0.02, k)

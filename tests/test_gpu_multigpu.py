@@ -71,3 +71,31 @@ def test_two_slabs_equal_one_gpu_at_4096(cuda_lib):
     run_ranks(2, body)
     for name, _ in P.F32_FIELDS:
         assert P.bits_equal(assemble(two, name), one.download(name)), name
+
+
+@pytest.mark.parametrize("world,n,k", [(2, 1024, 9), (8, 2048, 12)])
+def test_red_black_slabs_match_the_restatement(oracle, cuda_lib, world, n, k):
+    """k_rb_reg over row slabs: the first launch reads ghost rows copied by k_halo_exchange, the later ones ghost rows
+    the neighbours' k_rb_reg pushed over NVLink itself.  Bit-identical to the one-domain red-black restatement."""
+    if ndev(cuda_lib) < world:
+        pytest.skip(f"needs {world} GPUs")
+    rects = P.random_rects(n, 10, n + 3 * world)
+    fluids = make(cuda_lib, world, n, k, rects, mode="red_black")
+    ref = oracle.RefFluid(n, 0.02, k)
+    for r in rects:
+        ref.fill_rect(*r)
+    rng = np.random.default_rng(world)
+    for orient in (P.ROW, P.COL, P.PASSIVE):
+        x, x0 = P.rnd(rng, n), P.rnd(rng, n)
+        for f in fluids:
+            f.upload("velocities_x", x)
+            f.upload("velocities_x0", x0)
+
+        def body(r, barrier):
+            fluids[r].op_lin_solve(orient, "velocities_x", "velocities_x0", 0.37, 2.48, k)
+            fluids[r].sync()
+
+        run_ranks(world, body)
+        oracle.lin_solve(orient, x, x0, 0.37, 2.48, k, ref.cells, red_black=True)
+        got = assemble(fluids, "velocities_x")
+        assert P.bits_equal(got, x), f"orient {orient}: {P.describe_diff(got, x)}"
