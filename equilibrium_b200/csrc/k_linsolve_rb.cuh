@@ -174,7 +174,9 @@ __global__ void __launch_bounds__(RB_THREADS) k_rb_tiled(const float *__restrict
 // ---------------------------------------------------------------------------------------------
 #define RBR_T RB_T
 #define RBR_HALO RB_H                       // 12
-#define RBR_WARPS 4
+#ifndef RBR_WARPS
+#define RBR_WARPS 4                         // warps (64-column strips) per CTA
+#endif
 #define RBR_THREADS (32 * RBR_WARPS)
 #define RBR_W (64 * RBR_WARPS)              // 256 columns per CTA
 #define RBR_H 64                            // rows per CTA, all of them in registers
@@ -189,7 +191,7 @@ __global__ void __launch_bounds__(RB_THREADS) k_rb_tiled(const float *__restrict
 #define RBR_DIR_UP 3u
 #define RBR_DIR_DOWN 4u
 
-__global__ void __launch_bounds__(RBR_THREADS, 2) k_rb_reg(const float *__restrict__ xin, float *__restrict__ xout,
+__global__ void __launch_bounds__(RBR_THREADS, 8 / RBR_WARPS) k_rb_reg(const float *__restrict__ xin, float *__restrict__ xout,
                                                            const float *__restrict__ x0, const uint8_t *__restrict__ codes,
                                                            const uint8_t *__restrict__ chunk_flags,
                                                            const uint8_t *__restrict__ row_fluid,

@@ -5,8 +5,9 @@ pressure-solve convergence logged.
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29519 \
         scripts/c5_sweep.py [--size 32768] [--ks 20,80,200] [--mode red_black] [--frames 2] [--out gpurun_out/c5.json]
 
-Per K: a fresh fluid in the analytic initial state of SURVEY.md 8d (vx = sin(2 pi y / N), vy = sin(2 pi x / N), a
-checker-block density: the reference's uniform v = (1,1) start is nearly divergence-free away from the walls),
+Per K: a fresh fluid in an analytic, NON-solenoidal initial state (vx = sin(2 pi x / N), vy = sin(2 pi y / N): its
+divergence is (2 pi / N)(cos + cos), so the pressure solve has real work to do -- the reference's uniform v = (1,1)
+start and SURVEY 8d's sin(y), sin(x) pair are divergence-free away from the walls) with a checker-block density,
 `frames` frames timed on the device (max over ranks), then
   * div_l2      = || div(u) ||_2 of the velocity the step leaves behind (eq_divergence_l2, stencil of fluid.rs:341-345)
   * gs_residual = || 4 p - (sum of the 4 neighbours) - div ||_2 of the LAST pressure solve (project #2 keeps p in
@@ -61,8 +62,8 @@ def main():
         # analytic initial state on the owned rows
         x = np.arange(n, dtype=np.float64)
         y = np.arange(r0, r1, dtype=np.float64)
-        vx = np.broadcast_to(np.sin(2 * np.pi * y / n)[:, None], (rows, n)).astype(np.float32)
-        vy = np.broadcast_to(np.sin(2 * np.pi * x / n)[None, :], (rows, n)).astype(np.float32)
+        vx = np.broadcast_to(np.sin(2 * np.pi * x / n)[None, :], (rows, n)).astype(np.float32)
+        vy = np.broadcast_to(np.sin(2 * np.pi * y / n)[:, None], (rows, n)).astype(np.float32)
         blk = max(1, n // 64)
         dens = ((((np.arange(r0, r1) // blk)[:, None] + (np.arange(n) // blk)[None, :]) & 1) * 0.9).astype(np.float32)
         lib = f._lib
@@ -71,6 +72,7 @@ def main():
             a = np.ascontiguousarray(arr)
             L.check(lib, lib.eq_upload_rows(f._h, f.FIELDS[name], r0, rows, a.ctypes.data))
         del vx, vy, dens
+        div0 = reduce([f.divergence_l2() ** 2], "sum")[0] ** 0.5      # || div(u) ||_2 of the initial state
         f.step_n(1)                                   # warm-up frame (tables, first-touch)
         f.sync()
         if world > 1:
@@ -99,7 +101,7 @@ def main():
         rec = {"config": "c5", "size": n, "gs_iterations": k, "mode": args.mode, "n_gpus": world, "frames": args.frames,
                "ms_per_frame": ms / args.frames, "cell_updates_per_s": n * n * args.frames / (ms * 1e-3),
                "cell_updates_per_s_per_gpu": n * n * args.frames / (ms * 1e-3) / world,
-               "div_l2_after_step": d2 ** 0.5, "gs_residual_l2_last_pressure_solve": res2 ** 0.5}
+               "div_l2_initial": div0, "div_l2_after_step": d2 ** 0.5, "gs_residual_l2_last_pressure_solve": res2 ** 0.5}
         results.append(rec)
         if rank == 0:
             print(json.dumps(rec), flush=True)
