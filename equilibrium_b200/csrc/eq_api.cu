@@ -575,7 +575,7 @@ static int lin_solve_exact_tb(eq_fluid *h, const LinSolveReq *req, int nreq, int
         CU(cudaMemsetAsync(h->flags, 0, sizeof(unsigned), h->stream));
         CU(cudaMemsetAsync(h->flags + 8, 0, (size_t)nreq * prog_words * sizeof(unsigned), h->stream));
         const int grid = std::min(h->tb_ctas, p.njobs * nreq);
-        EQ_LAUNCH(k_linsolve_tb, grid, LSX_THREADS, TBX_SMEM_BYTES, h->stream, p);
+        EQ_LAUNCH(k_linsolve_tb, grid, TBX_THREADS, TBX_SMEM_BYTES, h->stream, p);
         TRY(check_launch("k_linsolve_tb"));
         done += kc;
     }
@@ -853,7 +853,7 @@ static int alloc_handle(const EqParams *params, eq_fluid **out) {
     {
         CU(cudaFuncSetAttribute(k_linsolve_tb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TBX_SMEM_BYTES));
         int tb_per_sm = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tb_per_sm, k_linsolve_tb, LSX_THREADS, TBX_SMEM_BYTES));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tb_per_sm, k_linsolve_tb, TBX_THREADS, TBX_SMEM_BYTES));
         h->tb_ctas = std::max(1, tb_per_sm) * h->sm_count;
     }
     if (const char *e = getenv("EQ_LSX_CTAS_PER_SM")) h->lsx_ctas = std::max(1, std::min(per_sm, atoi(e))) * h->sm_count;

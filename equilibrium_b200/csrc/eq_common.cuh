@@ -142,6 +142,10 @@ __device__ __forceinline__ void cp_async_16s(uint32_t saddr, const void *gmem) {
 __device__ __forceinline__ void cp_async_4s(uint32_t saddr, const void *gmem) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(saddr), "l"(gmem) : "memory");
 }
+// named barrier over a subset of the CTA's warps (all `nthreads` threads must call it)
+__device__ __forceinline__ void eq_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 // pull a line into L2 ahead of time (no register, no shared memory)
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // mbarrier (shared::cta) -- each barrier gets a 16-byte slot (8 used on the device)

@@ -27,7 +27,21 @@
 #ifndef TBX_T
 #define TBX_T 2                                   // iterations per job
 #endif
-#define TBX_LAG 2                                 // columns between consecutive sub-steps
+// TBX_SPLIT = 1: one compute warp PER SUB-STEP.  The per-job limit of the fused kernel is the instruction stream of
+// its single compute warp (~62 instructions per step for two sub-steps; one warp issues well below one instruction per
+// cycle), not the latency of the SHFL -> FP chain.  With the sub-steps a whole chunk apart (TBX_LAG >= LSX_CW + 2)
+// everything sub-step t+1 reads in macro step m was finalised by sub-step t in macro step m-1 at the latest, and what
+// either writes in a macro step lies outside the columns the other reads in it, so the two warps run the same macro
+// step concurrently and only meet at a named barrier between macro steps.
+#ifndef TBX_SPLIT
+#define TBX_SPLIT 0
+#endif
+#ifndef TBX_LAG
+#define TBX_LAG (TBX_SPLIT ? (EQ_LSX_CW + 2) : 2)  // columns between consecutive sub-steps
+#endif
+static_assert(!TBX_SPLIT || (TBX_T == 2 && TBX_LAG >= EQ_LSX_CW + 2), "TBX_SPLIT: two sub-steps, a whole chunk apart");
+#define TBX_CWARPS (TBX_SPLIT ? TBX_T : 1)         // compute warps per CTA
+#define TBX_THREADS (32 * (3 + TBX_CWARPS))        // + loader, storer, publisher
 #ifndef TBX_SLOTS
 #define TBX_SLOTS 8                               // chunks in the staging ring (power of two)
 #endif
@@ -46,7 +60,8 @@
 #define TBX_RAWOUT_OFF (TBX_RAWIN_OFF + TBX_T * TBX_ROWB)     // T rings: R of my last row, per sub-step
 #define TBX_BAR_OFF (TBX_RAWOUT_OFF + TBX_T * TBX_ROWB)
 #define TBX_MISC_OFF (TBX_BAR_OFF + 3u * TBX_SLOTS * 16u)
-#define TBX_SMEM_BYTES (TBX_MISC_OFF + 16u)
+#define TBX_AB_OFF (TBX_MISC_OFF + 16u)                       // mbarrier the compute warps meet at between macro steps
+#define TBX_SMEM_BYTES (TBX_AB_OFF + 16u)
 
 struct TbxProblem {
     float *x;
@@ -292,6 +307,8 @@ struct TbxJob {
     }
 
     // ------------------------------------------------------------------ COMPUTE warp
+    // TSEL < 0: this warp runs every sub-step; TSEL = t: only sub-step t (TBX_SPLIT)
+    template <int TSEL>
     __device__ __forceinline__ bool run_compute() const {
         const float a = pr.a, c_recip = pr.c_recip;
         float *__restrict__ x = pr.x;
@@ -350,6 +367,7 @@ struct TbxJob {
             float right[TBX_T], down[TBX_T], x0v[TBX_T], topv[TBX_T];
 #pragma unroll
             for (int t = 0; t < TBX_T; ++t) {
+                if (TSEL >= 0 && t != TSEL) continue;
                 const uint32_t o = (ob - 4u * TBX_LAG * t) & TBX_OMASK;
                 right[t] = lds_f32(xs_row[t] + ((o + 4u) & TBX_OMASK));
                 down[t] = lds_f32(down_row[t] + o);
@@ -366,9 +384,11 @@ struct TbxJob {
                 float up[TBX_T], right_n[TBX_T], down_n[TBX_T], x0_n[TBX_T], self[TBX_T], below[TBX_T];
                 unsigned code[TBX_T];
 #pragma unroll
-                for (int t = 0; t < TBX_T; ++t) up[t] = __shfl_up_sync(0xffffffffu, cur[t], 1);
+                for (int t = 0; t < TBX_T; ++t)
+                    if (TSEL < 0 || t == TSEL) up[t] = __shfl_up_sync(0xffffffffu, cur[t], 1);
 #pragma unroll
                 for (int t = 0; t < TBX_T; ++t) {
+                    if (TSEL >= 0 && t != TSEL) continue;
                     const uint32_t o = (ob + 4u * i - 4u * TBX_LAG * t) & TBX_OMASK;
                     const uint32_t o1 = (o + 4u) & TBX_OMASK, o2 = (o + 8u) & TBX_OMASK, om1 = (o - 4u) & TBX_OMASK;
                     right_n[t] = lds_f32(xs_row[t] + o2);
@@ -392,6 +412,7 @@ struct TbxJob {
                 // Phase B: arithmetic and the stores of the step
 #pragma unroll
                 for (int t = 0; t < TBX_T; ++t) {
+                    if (TSEL >= 0 && t != TSEL) continue;
                     const int c = cb + i - TBX_LAG * t;
                     const uint32_t o = (ob + 4u * i - 4u * TBX_LAG * t) & TBX_OMASK;
                     const uint32_t om1 = (o - 4u) & TBX_OMASK;
@@ -440,6 +461,7 @@ struct TbxJob {
             for (int s = LSX_CW * m_cur; s < s_end; ++s) {
 #pragma unroll
                 for (int t = 0; t < TBX_T; ++t) {
+                    if (TSEL >= 0 && t != TSEL) continue;
                     if (t < nsub) {
                         const int c = s - lane - TBX_LAG * t;       // column this lane computes now (0 = left frame cell)
                         const int cf = c - 1;                        // column finalised now
@@ -506,7 +528,7 @@ struct TbxJob {
         };
 
         if (!lsx_wait_bar(bar_full(0), 0u, p.error, lane)) return false;
-        if (p.jobtimes && lane == 0 && &pr == &p.prob[0]) p.jobtimes[4 * ((size_t)g * NBP + b) + 1] = lsx_gtime();
+        if (TSEL <= 0 && p.jobtimes && lane == 0 && &pr == &p.prob[0]) p.jobtimes[4 * ((size_t)g * NBP + b) + 1] = lsx_gtime();
         for (int m = 0; m < M; ++m) {
             if (m + 1 < NC && !lsx_wait_bar(bar_full(m + 1), use_parity(m + 1), p.error, lane)) return false;
             TBX_TRACE(2, m);
@@ -524,6 +546,7 @@ struct TbxJob {
                 for (int s = LSX_CW * m; s < s_end; ++s) {
 #pragma unroll
                     for (int t = 0; t < TBX_T; ++t) {
+                        if (TSEL >= 0 && t != TSEL) continue;
                         if (t < nsub) {
                             const uint32_t o = ((uint32_t)(s - lane - TBX_LAG * t) & TBX_CMASK) << 2;
                             const uint32_t o1 = (o + 4u) & TBX_OMASK, om1 = (o - 4u) & TBX_OMASK;
@@ -557,24 +580,33 @@ struct TbxJob {
                 general_steps(std::false_type{});
             }
             TBX_TRACE(3, m);
-            if (m >= TBX_BACK && m - TBX_BACK < NC && lane == 0) mbar_arrive(bar_done(m - TBX_BACK));
+            if (TSEL >= 0) {
+                // the compute warps meet between macro steps (an mbarrier rather than bar.sync: its wait has the
+                // watchdog and sees the error flag, so a failing warp can never leave the other one stuck)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(sbase + TBX_AB_OFF);
+                if (!lsx_wait_bar(sbase + TBX_AB_OFF, (uint32_t)(m & 1), p.error, lane)) return false;
+            }
+            if (TSEL <= 0 && m >= TBX_BACK && m - TBX_BACK < NC && lane == 0) mbar_arrive(bar_done(m - TBX_BACK));
         }
-        if (lane == 0)
+        if (TSEL <= 0 && lane == 0)
             for (int q = max(M - TBX_BACK, 0); q < NC; ++q) mbar_arrive(bar_done(q));
         return true;
     }
 };
 
-__global__ void __launch_bounds__(LSX_THREADS, 5) k_linsolve_tb(const TbxParams p) {
+__global__ void __launch_bounds__(TBX_THREADS, 5) k_linsolve_tb(const TbxParams p) {
     EQ_DYN_SMEM(tbx_smem_raw);
     const uint32_t sbase = smem_u32(tbx_smem_raw);
     const int total = p.njobs * p.nprob;
     const int lane = (int)threadIdx.x & 31;
-    if (threadIdx.x == 0) sts_u32(sbase + TBX_MISC_OFF + 8u, p.rotate_roles ? eq_cta_slot_rotation() : 0u);
+    if (threadIdx.x == 0) sts_u32(sbase + TBX_MISC_OFF + 8u, (p.rotate_roles && !TBX_SPLIT) ? eq_cta_slot_rotation() : 0u);
     __syncthreads();
     // role 0 compute, 1 loader, 2 storer, 3 publisher (uniform per warp: taken through a shuffle so that
     // the compiler keeps the dispatch branch-uniform)
-    const int warp = __shfl_sync(0xffffffffu, (((int)threadIdx.x >> 5) - (int)lds_u32(sbase + TBX_MISC_OFF + 8u)) & 3, 0);
+    // (TBX_SPLIT: warps 4.. are the compute warps of sub-steps 1..; 5-warp CTAs already land on rotating schedulers)
+    const int wraw = (int)threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, wraw < 4 ? ((wraw - (int)lds_u32(sbase + TBX_MISC_OFF + 8u)) & 3) : wraw, 0);
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -586,6 +618,7 @@ __global__ void __launch_bounds__(LSX_THREADS, 5) k_linsolve_tb(const TbxParams 
                 mbar_init(sbase + TBX_BAR_OFF + (uint32_t)(TBX_SLOTS + i) * 16u, 1u);
                 mbar_init(sbase + TBX_BAR_OFF + (uint32_t)(2 * TBX_SLOTS + i) * 16u, 1u);
             }
+            mbar_init(sbase + TBX_AB_OFF, (uint32_t)TBX_CWARPS);
         }
         __syncthreads();
         const unsigned t = lds_u32(sbase + TBX_MISC_OFF);
@@ -605,10 +638,11 @@ __global__ void __launch_bounds__(LSX_THREADS, 5) k_linsolve_tb(const TbxParams 
 #define TBX_DISPATCH(O)                                           \
     {                                                             \
         const TbxJob<O> job(p, pr, sbase, b, g, lane);            \
-        if (warp == 0) job.run_compute();                         \
+        if (warp == 0) job.template run_compute<TBX_SPLIT ? 0 : -1>();   \
         else if (warp == 1) job.run_loader();                     \
         else if (warp == 2) job.run_storer();                     \
-        else job.run_publisher();                                 \
+        else if (warp == 3) job.run_publisher();                  \
+        else job.template run_compute<TBX_SPLIT ? 1 : -1>();      \
     }
         if (pr.orient == EQ_ADJUST_ROW) TBX_DISPATCH(EQ_ADJUST_ROW)
         else if (pr.orient == EQ_ADJUST_COLUMN) TBX_DISPATCH(EQ_ADJUST_COLUMN)

@@ -32,6 +32,10 @@ def main():
     ap.add_argument("--ks", default="20,80,200")
     ap.add_argument("--mode", default="red_black", choices=["red_black", "exact"])
     ap.add_argument("--frames", type=int, default=2)
+    ap.add_argument("--viscosity", type=float, default=0.0,
+                    help="0 (default): diffusion is the identity (a = 0) and the velocity survives, so the projection has "
+                         "work to do; with the reference's 0.001 the diffusion number dt*visc*(N-2)^2 is 21 474 at this size "
+                         "and K sweeps from the stale zero guess (quirk Q3) wipe the velocity out in one frame")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "c5.json"))
     args = ap.parse_args()
     from equilibrium_b200 import Fluid, FluidConfigs, SimulationConfigs, connect_distributed
@@ -53,7 +57,7 @@ def main():
     n = args.size
     results = []
     for k in [int(x) for x in args.ks.split(",")]:
-        f = Fluid(FluidConfigs(diffusion=0.0, viscousity=0.001), SimulationConfigs(0.02, k, n), mode=args.mode,
+        f = Fluid(FluidConfigs(diffusion=0.0, viscousity=args.viscosity), SimulationConfigs(0.02, k, n), mode=args.mode,
                   device=local, rank=rank, world=world)
         if world > 1:
             connect_distributed(f)
@@ -98,7 +102,7 @@ def main():
             res2 += float(np.sum(r * r))
         del p, dv
         d2, res2 = reduce([d2, res2], "sum")
-        rec = {"config": "c5", "size": n, "gs_iterations": k, "mode": args.mode, "n_gpus": world, "frames": args.frames,
+        rec = {"config": "c5", "size": n, "gs_iterations": k, "viscosity": args.viscosity, "mode": args.mode, "n_gpus": world, "frames": args.frames,
                "ms_per_frame": ms / args.frames, "cell_updates_per_s": n * n * args.frames / (ms * 1e-3),
                "cell_updates_per_s_per_gpu": n * n * args.frames / (ms * 1e-3) / world,
                "div_l2_initial": div0, "div_l2_after_step": d2 ** 0.5, "gs_residual_l2_last_pressure_solve": res2 ** 0.5}

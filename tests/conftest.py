@@ -46,9 +46,11 @@ def emu_lib():
 
 @pytest.fixture(scope="session")
 def cuda_lib():
-    """The real library; GPU tests must run through it (no fallback)."""
-    assert os.path.exists(CUDA_LIB), "build libequilibrium_cuda.so first (__graft_entry__.build())"
+    """The real library; GPU tests must run through it (no fallback).  EQUILIBRIUM_CUDA_LIB selects another build of
+    the same sources (kernel variants under test)."""
+    path = os.path.abspath(os.environ.get("EQUILIBRIUM_CUDA_LIB") or CUDA_LIB)
+    assert os.path.exists(path), "build libequilibrium_cuda.so first (__graft_entry__.build())"
     from equilibrium_b200 import _lib
-    lib = _lib.load(CUDA_LIB)
+    lib = _lib.load(path)
     assert lib.eq_device_count() > 0, "no CUDA device visible"
-    return CUDA_LIB
+    return path

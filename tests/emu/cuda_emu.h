@@ -55,7 +55,10 @@ struct BlockState {
     std::vector<std::unique_ptr<WarpState>> warps;
     std::vector<unsigned char> dyn_smem;
     std::atomic<int> or_acc{0};
-    explicit BlockState(int n) : bar(n) {}
+    std::atomic<int> nb_count[16], nb_gen[16];          // named barriers (bar.sync id, nthreads)
+    explicit BlockState(int n) : bar(n) {
+        for (int i = 0; i < 16; ++i) { nb_count[i].store(0); nb_gen[i].store(0); }
+    }
 };
 struct Ctx {
     uint3_emu tid, bid;
@@ -86,6 +89,17 @@ static inline void __syncwarp(unsigned = 0xffffffffu) {
 }
 static inline void __syncthreads() {
     if (eq_emu::ctx.block) eq_emu::ctx.block->bar.arrive_and_wait();
+}
+// bar.sync id, nthreads: sense-reversing barrier over `nthreads` threads of the block
+static inline void eq_bar_sync(int id, int nthreads) {
+    eq_emu::BlockState *b = eq_emu::ctx.block;
+    const int gen = b->nb_gen[id].load(std::memory_order_acquire);
+    if (b->nb_count[id].fetch_add(1, std::memory_order_acq_rel) + 1 == nthreads) {
+        b->nb_count[id].store(0, std::memory_order_relaxed);
+        b->nb_gen[id].fetch_add(1, std::memory_order_release);
+    } else {
+        while (b->nb_gen[id].load(std::memory_order_acquire) == gen) std::this_thread::yield();
+    }
 }
 static inline int __syncthreads_or(int v) {
     eq_emu::BlockState *b = eq_emu::ctx.block;
