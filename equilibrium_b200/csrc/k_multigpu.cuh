@@ -9,7 +9,11 @@
 #include "eq_common.cuh"
 
 #define EQ_SYNC_WORDS 32          // [0..3] halo slots (up A/B, down A/B), [8..15] all-rank barrier
+#ifdef EQ_HOST_EMU
+#define EQ_XGPU_SPIN_LIMIT (1u << 30)   // emulated ranks are OS threads on a few cores: a spin is a yield, not 100 ns
+#else
 #define EQ_XGPU_SPIN_LIMIT (1u << 24)
+#endif
 
 struct EqHaloArgs {
     float *field;                 // my copy
