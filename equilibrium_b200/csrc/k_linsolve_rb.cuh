@@ -434,15 +434,29 @@ __global__ void __launch_bounds__(RBR_THREADS, 8 / RBR_WARPS) k_rb_reg(const flo
                 const size_t o = (size_t)gy * P + gx;
                 if (in1) *reinterpret_cast<float2 *>(xout + o) = make_float2(v[y][0], v[y][1]);
                 else xout[o] = v[y][0];
-                // row slabs: my first / last RBR_HALO rows are the neighbours' ghost rows for the next launch --
-                // written straight into their copy of xout over NVLink (no separate copy kernel, only a barrier)
-                float *peer = (peer_up_out && gy < row_lo + RBR_HALO) ? peer_up_out
-                            : ((peer_down_out && gy >= row_hi - RBR_HALO) ? peer_down_out : nullptr);
-                if (peer) {
-                    if (in1) *reinterpret_cast<float2 *>(peer + o) = make_float2(v[y][0], v[y][1]);
-                    else peer[o] = v[y][0];
-                }
             }
         }
     }
+#ifndef RBR_NO_PUSH
+    // Row slabs: my first / last RBR_HALO rows are the neighbours' ghost rows for the next launch.  The tiles that
+    // produce them write them straight into the neighbours' copy of xout over NVLink, so that the exchange between
+    // two launches is only a barrier.  A separate, block-uniform branch: folded into the write-out loop above, the
+    // extra selects cost the single-GPU kernel 15 % (11.1 -> 13.0 ms per 16384^2 solve).
+    const int gy_lo = gy0 + RBR_HALO, gy_hi = gy0 + RBR_H - RBR_HALO;      // output rows of this tile
+    const bool push_up = peer_up_out && gy_lo < row_lo + RBR_HALO && gy_hi > row_lo;
+    const bool push_down = peer_down_out && gy_hi > row_hi - RBR_HALO && gy_lo < row_hi;
+    if ((push_up || push_down) && lx >= RBR_HALO && lx < RBR_W - RBR_HALO && in0) {
+#pragma unroll
+        for (int y = RBR_HALO; y < RBR_H - RBR_HALO; ++y) {
+            const int gy = gy0 + y;
+            if (gy < row_lo || gy >= row_hi || gy >= N) continue;
+            float *peer = (push_up && gy < row_lo + RBR_HALO) ? peer_up_out : ((push_down && gy >= row_hi - RBR_HALO) ? peer_down_out : nullptr);
+            if (peer) {
+                const size_t o = (size_t)gy * P + gx;
+                if (in1) *reinterpret_cast<float2 *>(peer + o) = make_float2(v[y][0], v[y][1]);
+                else peer[o] = v[y][0];
+            }
+        }
+    }
+#endif
 }
