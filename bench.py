@@ -13,9 +13,11 @@ Workloads (BASELINE.json configs):
 The same workload is used for every --gpus value so the driver's scaling series is a
 strong-scaling series (row slabs, halo exchange per sweep).
 
-JSON line keys beyond the base contract: roofline (dominant kernel = lin_solve),
-cpu_baseline (the CPU oracle on one host core, bounded sample), red_black (the fast
-path on the same workload), clocks, e2e, gpu_launches.
+JSON line keys beyond the base contract: roofline (dominant kernel = the exact lin_solve), cpu_baseline (the CPU
+oracle on one host core, bounded sample), red_black (the red-black mode on the same workload: value, phases and
+its own roofline object), clocks, gpu_launches, e2e (the reference's frame loop through the public API: source
+record in, density frame out through the pinned-memory snapshot path) and e2e_full_mirror (all pub fields up and
+down around every step).
 """
 from __future__ import annotations
 
