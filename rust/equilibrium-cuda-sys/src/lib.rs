@@ -34,6 +34,19 @@ pub struct EqSource {
     pub d_density: f32,
 }
 
+/// Colours of render_image (renderer_helpers.rs:122-143): r, g, b, a bytes.
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct EqColors {
+    pub world: [u8; 4],
+    pub fluid: [u8; 4],
+    pub obstacle: [u8; 4],
+}
+
+pub const EQ_SNAP_DENSITY: c_int = 0;
+pub const EQ_SNAP_RGBA: c_int = 1;
+pub const EQ_SNAPSHOT_SLOTS: c_int = 2;
+
 pub const EQ_OK: c_int = 0;
 pub const EQ_MODE_EXACT: i32 = 0;
 pub const EQ_MODE_RED_BLACK: i32 = 1;
@@ -65,4 +78,11 @@ extern "C" {
     pub fn eq_sync(h: *mut eq_fluid) -> c_int;
     pub fn eq_upload(h: *mut eq_fluid, field: c_int, host: *const c_void, bytes: usize) -> c_int;
     pub fn eq_download(h: *mut eq_fluid, field: c_int, host: *mut c_void, bytes: usize) -> c_int;
+    // the frame hand-off (renderer_helpers.rs:61-65, 145-167), see INTEGRATION.md section 4
+    pub fn eq_snapshot_begin(h: *mut eq_fluid, kind: c_int, slot: c_int, colors: *const EqColors,
+                             host_dst: *mut c_void, bytes: usize) -> c_int;
+    pub fn eq_snapshot_wait(h: *mut eq_fluid, slot: c_int) -> c_int;
+    pub fn eq_render_rgba(h: *mut eq_fluid, colors: *const EqColors, host_rgba: *mut c_void, bytes: usize) -> c_int;
+    pub fn eq_host_alloc(out: *mut *mut c_void, bytes: usize) -> c_int;
+    pub fn eq_host_free(p: *mut c_void) -> c_int;
 }

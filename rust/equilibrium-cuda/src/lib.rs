@@ -57,6 +57,39 @@ impl CudaFluid {
     }
 }
 
+/// A frame buffer in pinned host memory (eq_host_alloc) for the snapshot path.
+pub struct PinnedFrame {
+    ptr: *mut c_void,
+    bytes: usize,
+}
+unsafe impl Send for PinnedFrame {}
+impl PinnedFrame {
+    pub fn new(bytes: usize) -> Self {
+        let mut ptr = std::ptr::null_mut();
+        check(unsafe { sys::eq_host_alloc(&mut ptr, bytes) });
+        PinnedFrame { ptr, bytes }
+    }
+    pub fn as_bytes(&self) -> &[u8] { unsafe { std::slice::from_raw_parts(self.ptr as *const u8, self.bytes) } }
+    pub fn as_f32(&self) -> &[f32] { unsafe { std::slice::from_raw_parts(self.ptr as *const f32, self.bytes / 4) } }
+}
+impl Drop for PinnedFrame {
+    fn drop(&mut self) { unsafe { sys::eq_host_free(self.ptr); } }
+}
+
+impl CudaFluid {
+    /// What `fluid.clone()` + `tx.send` is for the render thread (renderer_helpers.rs:61-65): start an asynchronous
+    /// snapshot of the current frame (f32 density, or RGBA pixels by render_image's rule, renderer_helpers.rs:145-167)
+    /// into `dst`; later steps may run while it is in flight.  `dst` must not be read before `snapshot_wait(slot)`.
+    pub fn snapshot_begin(&mut self, rgba: Option<&sys::EqColors>, slot: i32, dst: &mut PinnedFrame) {
+        let (kind, colors) = match rgba {
+            Some(c) => (sys::EQ_SNAP_RGBA, c as *const sys::EqColors),
+            None => (sys::EQ_SNAP_DENSITY, std::ptr::null()),
+        };
+        check(unsafe { sys::eq_snapshot_begin(self.h, kind, slot, colors, dst.ptr, dst.bytes) });
+    }
+    pub fn snapshot_wait(&mut self, slot: i32) { check(unsafe { sys::eq_snapshot_wait(self.h, slot) }); }
+}
+
 impl Clone for CudaFluid {
     /// #[derive(Clone)] (fluid.rs:51), used once per frame by the caller (renderer_helpers.rs:61-65)
     fn clone(&self) -> Self {

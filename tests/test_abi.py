@@ -64,3 +64,17 @@ def test_config_defaults_match_reference():
     s, f = SimulationConfigs(), FluidConfigs()
     assert (s.delta_t, s.frames, s.size) == (0.02, 16, 128)            # configs.rs:14-22
     assert (f.diffusion, f.viscousity, f.has_perlin_noise) == (0.0, 0.001, True)   # configs.rs:50-60
+
+
+def test_rust_sys_crate_binds_only_declared_symbols():
+    """rust/ cannot be compiled in this image (no cargo): at least keep its extern block inside the header."""
+    rs = open(os.path.join(ROOT, "rust", "equilibrium-cuda-sys", "src", "lib.rs")).read()
+    bound = set(re.findall(r"pub fn (eq_[a-z0-9_]+)\s*\(", rs))
+    assert bound and bound <= set(declared_symbols()), sorted(bound - set(declared_symbols()))
+    for needed in ("eq_create", "eq_step", "eq_fill_rect", "eq_add_velocity", "eq_clone", "eq_destroy", "eq_download",
+                   "eq_snapshot_begin", "eq_snapshot_wait"):
+        assert needed in bound, needed
+
+
+def test_colors_layout_matches_header():
+    assert C.sizeof(_lib.EqColors) == 12 and _lib.SNAPSHOT_SLOTS == 2
