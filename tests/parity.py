@@ -155,7 +155,7 @@ def check_render_and_snapshot(oracle, lib_path, n, rects, seed=0, steps=2):
     restatement of render_image's pixel loop (renderer_helpers.rs:145-167) on adversarial densities,
     then double-buffered snapshots taken between steps against plain downloads."""
     rng = np.random.default_rng(seed)
-    dev, ref = make_pair(oracle, lib_path, n, 2, rects)
+    dev, ref = make_pair(oracle, lib_path, n, 1, rects)
     d = (rng.standard_normal((n, n)) * 0.8).astype(np.float32)
     flat = d.reshape(-1)
     # zero / negative zero (world colour), saturation of `as u8` both ways, NaN (-> 0), infinities, denormals
@@ -169,26 +169,21 @@ def check_render_and_snapshot(oracle, lib_path, n, rects, seed=0, steps=2):
     got = dev.render_rgba(obstacle)
     assert got.shape == (n, n, 4)
     assert np.array_equal(got, want), f"render_rgba N={n}: {int((got != want).any(axis=2).sum())} pixels differ"
-    # snapshots: begin after each step, wait one step later (the copy overlaps the next step)
+    if steps <= 0:
+        return
+    # snapshots: begin after a step, wait one step later (the copy is in flight while the state moves on); the
+    # expectation is a plain download taken at the point of the snapshot
     bufs = [np.empty((n, n), dtype=np.float32), np.empty((n, n, 4), dtype=np.uint8)]
     dev.upload("density", np.nan_to_num(d, nan=0.5, posinf=2.0, neginf=-2.0))
-    expect = []
     for s in range(steps):
         dev.step()
         rgba = bool(s & 1)
         dev.snapshot_begin(bufs[s & 1], slot=s & 1, rgba=rgba, obstacles_color=obstacle)
+        dens = dev.download("density")
         dev.step()                                   # the state moves on while the snapshot is in flight
         dev.snapshot_wait(s & 1)
-        expect.append((rgba, bufs[s & 1].copy()))
-    # replay on a second handle with plain downloads
-    dev2, _ = make_pair(oracle, lib_path, n, 2, rects)
-    dev2.upload("density", np.nan_to_num(d, nan=0.5, posinf=2.0, neginf=-2.0))
-    for s in range(steps):
-        dev2.step()
-        dens = dev2.download("density")
-        rgba, snap = expect[s]
         if rgba:
-            assert np.array_equal(snap, oracle.render_rgba(dens, ref.cells, world, fluid, obstacle)), f"RGBA snapshot {s}"
+            assert np.array_equal(bufs[1], oracle.render_rgba(dens, ref.cells, world, fluid, obstacle)), f"RGBA snapshot {s}"
         else:
-            assert bits_equal(snap, dens), f"density snapshot {s}: {describe_diff(snap, dens)}"
-        dev2.step()
+            assert bits_equal(bufs[0], dens), f"density snapshot {s}: {describe_diff(bufs[0], dens)}"
+        assert not bits_equal(dens, dev.download("density")), "the second step did not change the state"
