@@ -59,7 +59,48 @@ def run(n, k, frames, rects, imp, checkpoints):
     return c, out
 
 
+WORLD, FLUID, OBSTACLE = (94, 146, 162, 128), (208, 88, 157, 220), (255, 0, 0, 255)   # configs.rs:56-57, Color32::RED
+
+
+def render_numpy(density, cells, world=WORLD, fluid=FLUID, obstacle=OBSTACLE):
+    """Second, vectorised restatement of render_image's pixel rule (renderer_helpers.rs:145-167) used to cross-check
+    oracle/fluid_ref.c: ref_render_rgba before its hash is committed."""
+    def as_u8(v):                                  # Rust `f32 as u8`: truncate, saturate, NaN -> 0
+        v = np.nan_to_num(v.astype(np.float32), nan=0.0, posinf=255.0, neginf=0.0)
+        return np.clip(np.trunc(v), 0, 255).astype(np.uint8)
+    out = np.empty(density.shape + (4,), dtype=np.uint8)
+    out[...] = np.array(world, dtype=np.uint8)
+    nz = (density != 0) & (cells == 0)
+    out[nz, 0] = as_u8(density * np.float32(fluid[0]))[nz]
+    out[nz, 1] = fluid[1]
+    out[nz, 2] = as_u8(density)[nz]
+    out[nz, 3] = 1
+    out[cells != 0] = np.array(obstacle, dtype=np.uint8)
+    return out
+
+
+def render_golden():
+    """Pixels of the default scene after 16 frames (the committed density) with the default colours."""
+    dens = np.load(os.path.join(HERE, "default_scene_density_f16.npy"))
+    c = O.RefFluid(128, 0.02, 16)
+    c.fill_rect(80, 80, 110, 110)
+    a = O.render_rgba(dens, c.cells, WORLD, FLUID, OBSTACLE)
+    b = render_numpy(dens, c.cells)
+    assert np.array_equal(a, b)
+    rec = {"note": "oracle-generated (C and numpy restatements of renderer_helpers.rs:145-167 agree); not reference output",
+           "scene": "default_128_k16, frame 16", "world": WORLD, "fluid": FLUID, "obstacle": OBSTACLE,
+           "sha256": sha(a), "obstacle_pixels": int((a == np.array(OBSTACLE, dtype=np.uint8)).all(axis=2).sum()),
+           "fluid_pixels": int((a[..., 3] == 1).sum())}
+    with open(os.path.join(HERE, "render_rgba.json"), "w") as f:
+        json.dump(rec, f, indent=1, sort_keys=True)
+    print("written", os.path.join(HERE, "render_rgba.json"))
+
+
 def main():
+    render_only = "--render-only" in sys.argv
+    if render_only:
+        render_golden()
+        return
     gold = {"note": "oracle-generated (both restatements agree); not reference outputs",
             "scenes": {}}
     rect = [(80, 80, 110, 110)]                     # obstacle.rs:47-51
@@ -76,6 +117,7 @@ def main():
     with open(os.path.join(HERE, "default_scene.json"), "w") as f:
         json.dump(gold, f, indent=1, sort_keys=True)
     print("written", os.path.join(HERE, "default_scene.json"))
+    render_golden()
 
 
 if __name__ == "__main__":

@@ -187,3 +187,28 @@ def check_render_and_snapshot(oracle, lib_path, n, rects, seed=0, steps=2):
         else:
             assert bits_equal(bufs[0], dens), f"density snapshot {s}: {describe_diff(bufs[0], dens)}"
         assert not bits_equal(dens, dev.download("density")), "the second step did not change the state"
+
+
+def golden_render_case():
+    """(density, rects, colours, record) of tests/golden/render_rgba.json: the default scene after 16 frames."""
+    import json
+    import os
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    with open(os.path.join(gold, "render_rgba.json")) as f:
+        rec = json.load(f)
+    dens = np.load(os.path.join(gold, "default_scene_density_f16.npy"))
+    return dens, [(80, 80, 110, 110)], rec
+
+
+def check_golden_render(lib_path):
+    """Device colour map of the committed default-scene density against the committed pixel hash (no oracle needed)."""
+    import hashlib
+    dens, rects, rec = golden_render_case()
+    n = dens.shape[0]
+    dev = Fluid(FluidConfigs(), SimulationConfigs(0.02, 16, n), lib_path=lib_path)
+    for (x0, y0, x1, y1) in rects:
+        dev.fill_obstacle(Rectangle((x0, y0), (x1, y1), n))
+    dev.upload("density", dens)
+    px = dev.render_rgba(tuple(rec["obstacle"]))
+    assert hashlib.sha256(np.ascontiguousarray(px).tobytes()).hexdigest() == rec["sha256"]
+    assert int((px == np.array(rec["obstacle"], dtype=np.uint8)).all(axis=2).sum()) == rec["obstacle_pixels"] == 1408

@@ -158,3 +158,7 @@ def test_red_black_tiled_across_tiles(oracle, emu_lib, orient, n):
 @pytest.mark.parametrize("n,steps", [(64, 1), (101, 0)])      # (the GPU suite runs more frames; emulated steps are slow)
 def test_render_rgba_and_snapshots(oracle, emu_lib, n, steps):
     P.check_render_and_snapshot(oracle, emu_lib, n, [(10, 10, 20, 30), (40, 5, 50, 60)], steps=steps)
+
+
+def test_render_rgba_golden_pixels(emu_lib):
+    P.check_golden_render(emu_lib)

@@ -189,3 +189,7 @@ def test_config4_16384_lin_solve_direct(oracle, cuda_lib):
 @pytest.mark.parametrize("n", [128, 1001])
 def test_render_rgba_and_snapshots(oracle, cuda_lib, n):
     P.check_render_and_snapshot(oracle, cuda_lib, n, P.random_rects(n, 6, 3))
+
+
+def test_render_rgba_golden_pixels(cuda_lib):
+    P.check_golden_render(cuda_lib)

@@ -154,3 +154,17 @@ def test_render_rgba_known_answers(oracle):
     assert px[5].tolist() == [0, 88, 0, 1]                 # NaN != 0.0 is true; NaN as u8 = 0
     assert px[6].tolist() == [94, 146, 162, 128]           # -0.0 == 0.0
     assert px[7].tolist() == [255, 0, 0, 255]              # wall
+
+
+def test_render_rgba_golden_pixels(oracle):
+    """The default scene after 16 frames through the pixel rule: committed hash, and the reference's own known answer
+    for that scene -- 1408 wall cells (renderer_helpers.rs:222-252) -- shows up as 1408 obstacle-coloured pixels."""
+    import parity as P
+    dens, rects, rec = P.golden_render_case()
+    ref = oracle.RefFluid(128, 0.02, 16)
+    for r in rects:
+        ref.fill_rect(*r)
+    px = oracle.render_rgba(dens, ref.cells, tuple(rec["world"]), tuple(rec["fluid"]), tuple(rec["obstacle"]))
+    assert hashlib.sha256(px.tobytes()).hexdigest() == rec["sha256"]
+    assert int((px == np.array(rec["obstacle"], dtype=np.uint8)).all(axis=2).sum()) == 1408
+    assert int((px[..., 3] == 1).sum()) == rec["fluid_pixels"]
