@@ -78,3 +78,24 @@ def test_rust_sys_crate_binds_only_declared_symbols():
 
 def test_colors_layout_matches_header():
     assert C.sizeof(_lib.EqColors) == 12 and _lib.SNAPSHOT_SLOTS == 2
+
+
+def test_no_fused_multiply_add_outside_the_division_routine():
+    """Bit-exactness needs every multiply and add rounded separately (rustc never contracts).  Static
+    check of the compiled SASS: FFMA may only appear in the kernels that divide (the correctly rounded __fdiv_rn
+    sequence of the divergence stencil, fluid.rs:341-345) -- never in a solver, advect or gradient kernel."""
+    import shutil
+    import subprocess
+    if not shutil.which("cuobjdump") or not os.path.exists(CUDA_LIB):
+        pytest.skip("needs cuobjdump and the built library")
+    sass = subprocess.run(["cuobjdump", "-sass", CUDA_LIB], capture_output=True, text=True, timeout=300).stdout
+    fn, with_fma, seen = None, set(), set()
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            fn = m.group(1)
+            seen.add(fn)
+        elif fn and re.search(r"\bFFMA\b", line):
+            with_fma.add(fn)
+    assert any("k_linsolve_tb" in f for f in seen) and any("k_rb_reg" in f for f in seen) and any("k_advect" in f for f in seen)
+    assert all("k_divergence" in f for f in with_fma), sorted(with_fma)
