@@ -172,6 +172,11 @@ struct TbxJob {
             if (!lsx_wait_flags(flag_prev, (unsigned)q + 1u, false, flag_above, (unsigned)q + 1u, false, p.error, lane)) return false;
             const uint32_t slot = (uint32_t)(q % TBX_SLOTS) * (LSX_CW * 4u);
             const int col0 = LSX_CW * q;
+#ifdef TBX_DBG_NOLOAD   // stage-isolation build (with EQ_LSX_NODEPS=1; WRONG results): the loader only signals
+            (void)x; (void)x0; (void)slot; (void)col0; (void)sub; (void)rr;
+            if (false)
+#endif
+            {
             // x: global rows j0 .. j0+32 hold F_{k0-1} (band 0 also needs the frame row 0)
             const int jx_lo = (b == 0) ? 0 : j0;
 #pragma unroll
@@ -221,6 +226,7 @@ struct TbxJob {
                     }
                 }
             }
+            }
             cp_async_mbar_arrive_noinc(bar_full(q));
             TBX_TRACE(1, q);
         }
@@ -239,6 +245,11 @@ struct TbxJob {
             TBX_TRACE(4, q);
             const uint32_t slot = (uint32_t)(q % TBX_SLOTS) * (LSX_CW * 4u);
             const int col0 = LSX_CW * q;
+#ifdef TBX_DBG_NOSTORE  // stage-isolation build (WRONG results): the storer only recycles the slots
+            (void)x; (void)slot; (void)col0; (void)sub; (void)rr; (void)jf; (void)has_below;
+            if (false)
+#endif
+            {
             // rows of the last sub-step (iteration k0+nsub-1); Passive also keeps the frame rows it touched
 #pragma unroll
             for (int pass = 0; pass < (34 + RPP - 1) / RPP; ++pass) {
@@ -266,6 +277,7 @@ struct TbxJob {
                         *reinterpret_cast<float4 *>(pr.raw + ((size_t)t * NBP + b + 1) * P + col0 + 4 * sub) = v;
                     }
                 }
+            }
             }
             __syncwarp();
             TBX_TRACE(5, q);
@@ -535,6 +547,11 @@ struct TbxJob {
             const int mode = macro_mode(m);
             m_cur = m;
             const int s_end = min(LSX_CW * m + LSX_CW, S);
+#ifdef TBX_DBG_NOCOMPUTE   // stage-isolation build (WRONG results): the compute warp only waits and signals
+            if (false) {
+            } else if (mode >= 0 && s_end >= 0) {
+            } else
+#endif
             if (nsub == TBX_T && mode == MODE_FAST) {
                 fast_steps(std::integral_constant<int, 0>{});
             } else if (nsub == TBX_T && mode == MODE_EDGE && lean_edges && edge_simple(m) && LSX_CW * m + LSX_CW - 1 <= N - 2) {
