@@ -122,7 +122,7 @@ struct eq_fluid {
     unsigned *peer_sync[EQ_MAX_RANKS];
     bool peer_ipc[EQ_MAX_RANKS];                 // mapped with cudaIpcOpenMemHandle (must be closed)
     unsigned *sync;                              // my cross-GPU sync slots
-    unsigned halo_epoch, bar_epoch;
+    unsigned halo_epoch, bar_epoch, rb_epoch;
     bool attached;
     // per-frame snapshots: staging slots, their events, the copy stream
     cudaStream_t copy_stream;
@@ -619,7 +619,11 @@ static int lin_solve_red_black(eq_fluid *h, const LinSolveReq *req, int nreq, in
             const int it = (int)std::min<int64_t>(RB_T, iters - done);
             // ghost rows of `cur`: copied by the exchange kernel before the first launch, pushed by k_rb_reg itself
             // afterwards (then the exchange is only the neighbour barrier: nrows = 0)
+#if RBR_INLINE_BARRIER
+            if (!pushed || use_tiled) TRY(halo_xchg(h, cur, RB_H));    // later launches wait on the neighbours' flags themselves
+#else
             TRY(halo_xchg(h, cur, pushed ? 0 : RB_H));
+#endif
             if (use_tiled) {
                 EQ_LAUNCH(k_rb_tiled, grid_t, RB_THREADS, RB_SMEM_BYTES, h->stream, cur, other, req[i].x0, h->codes,
                           h->row_fluid, h->col_fluid, req[i].a, c_recip, req[i].orient, it, L.row0, L.row1, L);
@@ -630,9 +634,25 @@ static int lin_solve_red_black(eq_fluid *h, const LinSolveReq *req, int nreq, in
                     TRY(peer_buffer(h, other, h->rank - 1, &pu));
                     TRY(peer_buffer(h, other, h->rank + 1, &pd));
                 }
+#if RBR_INLINE_BARRIER
+                RbrSync sy;
+                memset(&sy, 0, sizeof(sy));
+                if (h->world > 1) {
+                    sy.mine = h->sync;
+                    sy.up = h->rank > 0 ? h->peer_sync[h->rank - 1] : nullptr;
+                    sy.down = h->rank + 1 < h->world ? h->peer_sync[h->rank + 1] : nullptr;
+                    sy.epoch = ++h->rb_epoch;
+                    sy.wait_epoch = pushed ? sy.epoch - 1 : 0u;
+                    sy.error = reinterpret_cast<int *>(h->flags + 1);
+                }
+                EQ_LAUNCH(k_rb_reg, grid_r, RBR_THREADS, RBR_SMEM_BYTES, h->stream, cur, other, req[i].x0, h->codes,
+                          h->chunk_flags, h->row_fluid, h->col_fluid, req[i].a, c_recip, req[i].orient, it, L.row0, L.row1,
+                          ty0, pu, pd, L, sy);
+#else
                 EQ_LAUNCH(k_rb_reg, grid_r, RBR_THREADS, RBR_SMEM_BYTES, h->stream, cur, other, req[i].x0, h->codes,
                           h->chunk_flags, h->row_fluid, h->col_fluid, req[i].a, c_recip, req[i].orient, it, L.row0, L.row1,
                           ty0, pu, pd, L);
+#endif
                 TRY(check_launch("k_rb_reg"));
                 pushed = (h->world > 1);
             }

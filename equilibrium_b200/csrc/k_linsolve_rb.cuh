@@ -186,6 +186,33 @@ __global__ void __launch_bounds__(RB_THREADS) k_rb_tiled(const float *__restrict
 #define RBR_EDGE_OFF RBR_X0_BYTES           // float edge[RBR_WARPS][2][RBR_H]
 #define RBR_SMEM_BYTES (RBR_X0_BYTES + RBR_WARPS * 2u * RBR_H * 4u)
 
+// RBR_INLINE_BARRIER = 1 (opt-in, not yet measured on GPUs): no kernel at all between two launches of a row-slab
+// solve.  The tiles that read ghost rows wait, at their start, for the neighbour's "launch e-1 finished" flag; the last
+// CTA of a launch to finish raises that flag in both neighbours.  Interior tiles never wait, so the neighbour barrier
+// hides behind them.
+#ifndef RBR_INLINE_BARRIER
+#define RBR_INLINE_BARRIER 0
+#endif
+#if RBR_INLINE_BARRIER
+#include "k_multigpu.cuh"
+struct RbrSync {
+    unsigned *mine;        // my sync words: [16] raised by the rank above, [17] by the rank below, [20] CTA counter
+    unsigned *up, *down;   // the neighbours' sync words (nullptr at the ends / on one GPU)
+    unsigned epoch;        // number of this launch (the same on every rank)
+    unsigned wait_epoch;   // ghost rows are valid once the neighbours finished this launch; 0 = no wait (copied rows)
+    int *error;
+};
+#define RBR_SYNC_PARAM , RbrSync sy
+// ghost rows land in my memory while this kernel is already resident: read x through L2 (ld.global.cg), not through
+// the non-coherent path the compiler picks for a const __restrict__ pointer
+#define RBR_LD_X2(p) __ldcg(reinterpret_cast<const float2 *>(p))
+#define RBR_LD_X1(p) __ldcg(p)
+#else
+#define RBR_SYNC_PARAM
+#define RBR_LD_X2(p) (*reinterpret_cast<const float2 *>(p))
+#define RBR_LD_X1(p) (*(p))
+#endif
+
 #define RBR_DIR_LEFT 1u
 #define RBR_DIR_RIGHT 2u
 #define RBR_DIR_UP 3u
@@ -198,7 +225,7 @@ __global__ void __launch_bounds__(RBR_THREADS, 8 / RBR_WARPS) k_rb_reg(const flo
                                                            const uint8_t *__restrict__ col_fluid, float a, float c_recip,
                                                            int orient, int iters, int row_lo, int row_hi, int tile_y0,
                                                            float *__restrict__ peer_up_out, float *__restrict__ peer_down_out,
-                                                           EqLayout L) {
+                                                           EqLayout L RBR_SYNC_PARAM) {
     EQ_DYN_SMEM(rbr_smem);
     float *x0s = reinterpret_cast<float *>(rbr_smem);                    // [2][RBR_H][RBR_THREADS], thread-private slots
     float *edge = reinterpret_cast<float *>(rbr_smem + RBR_EDGE_OFF);     // [warp][side][row]
@@ -210,6 +237,19 @@ __global__ void __launch_bounds__(RBR_THREADS, 8 / RBR_WARPS) k_rb_reg(const flo
     const bool in0 = (gx >= 0 && gx < N), in1 = (gx + 1 >= 0 && gx + 1 < N);
     const bool colok0 = (gx >= 1 && gx <= N - 2), colok1 = (gx + 1 >= 1 && gx + 1 <= N - 2);
 
+#if RBR_INLINE_BARRIER
+    if (sy.wait_epoch) {
+        // tiles whose region reaches into the neighbours' rows read ghost rows the neighbours' previous launch pushed
+        const bool reads_up = sy.up && gy0 < row_lo, reads_down = sy.down && gy0 + RBR_H > row_hi;
+        if (reads_up || reads_down) {
+            if (tid == 0) {
+                if (reads_up) eq_xgpu_wait(sy.mine + 16, sy.wait_epoch, sy.error);
+                if (reads_down) eq_xgpu_wait(sy.mine + 17, sy.wait_epoch, sy.error);
+            }
+            __syncthreads();
+        }
+    }
+#endif
     float v[RBR_H][2];
     // ---- stage: x into registers, x0 into my shared-memory slots.  x0 goes global -> shared with cp.async (no
     // register in between: the 249 registers of this kernel leave none to batch loads in), so all of a thread's
@@ -225,7 +265,7 @@ __global__ void __launch_bounds__(RBR_THREADS, 8 / RBR_WARPS) k_rb_reg(const flo
         }
 #pragma unroll
         for (int y = 0; y < RBR_H; ++y) {
-            const float2 xv = *reinterpret_cast<const float2 *>(xin + o0 + (size_t)y * P);
+            const float2 xv = RBR_LD_X2(xin + o0 + (size_t)y * P);
             v[y][0] = xv.x;
             v[y][1] = xv.y;
         }
@@ -235,8 +275,8 @@ __global__ void __launch_bounds__(RBR_THREADS, 8 / RBR_WARPS) k_rb_reg(const flo
             const int gy = gy0 + y;
             const bool rowin = (gy >= 0 && gy < N);
             const size_t o = (size_t)gy * P + gx;                        // only dereferenced where rowin && in0 / in1
-            v[y][0] = (rowin && in0) ? xin[o] : 0.f;
-            v[y][1] = (rowin && in1) ? xin[o + 1] : 0.f;
+            v[y][0] = (rowin && in0) ? RBR_LD_X1(xin + o) : 0.f;
+            v[y][1] = (rowin && in1) ? RBR_LD_X1(xin + o + 1) : 0.f;
             if (rowin && in0) cp_async_4s(x0s_u32 + 4u * ((0 * RBR_H + y) * RBR_THREADS + tid), x0 + o);
             else x0s[(0 * RBR_H + y) * RBR_THREADS + tid] = 0.f;
             if (rowin && in1) cp_async_4s(x0s_u32 + 4u * ((1 * RBR_H + y) * RBR_THREADS + tid), x0 + o + 1);
@@ -455,6 +495,21 @@ __global__ void __launch_bounds__(RBR_THREADS, 8 / RBR_WARPS) k_rb_reg(const flo
                 const size_t o = (size_t)gy * P + gx;
                 if (in1) *reinterpret_cast<float2 *>(peer + o) = make_float2(v[y][0], v[y][1]);
                 else peer[o] = v[y][0];
+            }
+        }
+    }
+#endif
+#if RBR_INLINE_BARRIER
+    if (sy.up || sy.down) {
+        __threadfence_system();                    // my stores and pushes, before I count as finished
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned total = gridDim.x * gridDim.y;
+            if (atomicAdd(sy.mine + 20, 1u) == total - 1u) {   // the last CTA of the launch
+                __threadfence_system();
+                sy.mine[20] = 0u;                  // the next launch starts after this kernel (same stream)
+                if (sy.up) st_release_sys_u32(sy.up + 17, sy.epoch);       // I am the rank below my upper neighbour
+                if (sy.down) st_release_sys_u32(sy.down + 16, sy.epoch);   // ... and the rank above my lower one
             }
         }
     }

@@ -33,14 +33,17 @@ def oracle():
 
 @pytest.fixture(scope="session")
 def emu_lib():
-    """Product sources compiled against the host SIMT emulator (tests/emu)."""
+    """Product sources compiled against the host SIMT emulator (tests/emu).  EQUILIBRIUM_EMU_LIB selects another
+    emulated build of the same sources (kernel variants under test, e.g. -DRBR_INLINE_BARRIER=1)."""
+    os.environ.setdefault("EQ_EMU_SMS", "4")
+    if os.environ.get("EQUILIBRIUM_EMU_LIB"):
+        return os.path.abspath(os.environ["EQUILIBRIUM_EMU_LIB"])
     csrc = os.path.join(ROOT, "equilibrium_b200", "csrc")
     srcs = [os.path.join(csrc, f) for f in os.listdir(csrc)]
     srcs += [os.path.join(ROOT, "tests", "emu", f) for f in ("cuda_emu.h", "cuda_emu.cpp")]
     srcs.append(os.path.join(ROOT, "include", "equilibrium_cuda.h"))
     if _newer(EMU_LIB, srcs):
         subprocess.check_call([os.path.join(ROOT, "tests", "emu", "build_emu.sh")])
-    os.environ.setdefault("EQ_EMU_SMS", "4")
     return EMU_LIB
 
 

@@ -155,6 +155,8 @@ static inline int __all_sync(unsigned, int pred) {
     return all;
 }
 
+template <typename T>
+static inline T __ldcg(const T *p) { return *p; }
 static inline int __any_sync(unsigned m, int pred) { return !__all_sync(m, !pred); }
 
 // ---- memory model stand-ins --------------------------------------------------
