@@ -57,6 +57,11 @@ class EqProfile(C.Structure):
     ]
 
 
+class EqNoise(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("first_frame", C.c_uint64), ("cos_t", C.c_float), ("sin_t", C.c_float),
+                ("gain", C.c_float), ("reserved", C.c_float)]
+
+
 class EqColors(C.Structure):
     _fields_ = [("world", C.c_uint8 * 4), ("fluid", C.c_uint8 * 4), ("obstacle", C.c_uint8 * 4)]
 
@@ -90,6 +95,7 @@ SIGNATURES = {
     "eq_get_params": (C.c_int, [_H, C.POINTER(EqParams)]),
     "eq_step": (C.c_int, [_H]),
     "eq_step_n": (C.c_int, [_H, C.c_int64, C.POINTER(EqSource), C.c_int64]),
+    "eq_step_n_noise": (C.c_int, [_H, C.c_int64, C.POINTER(EqNoise)]),
     "eq_sync": (C.c_int, [_H]),
     "eq_upload": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_size_t]),
     "eq_download": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_size_t]),
@@ -101,6 +107,7 @@ SIGNATURES = {
     "eq_op_diffuse": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int64]),
     "eq_op_project": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64]),
     "eq_op_advect": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "eq_op_add_source": (C.c_int, [_H, C.c_int, C.c_int, C.c_float]),
     "eq_snapshot_begin": (C.c_int, [_H, C.c_int, C.c_int, C.POINTER(EqColors), C.c_void_p, C.c_size_t]),
     "eq_snapshot_wait": (C.c_int, [_H, C.c_int]),
     "eq_render_rgba": (C.c_int, [_H, C.POINTER(EqColors), C.c_void_p, C.c_size_t]),

@@ -1140,6 +1140,24 @@ int eq_step_n(eq_fluid *h, int64_t n, const EqSource *sources, int64_t n_sources
     return EQ_OK;
 }
 
+// add_noise on the device: frame f of this call gets the impulse of Philox counter first_frame + f
+int eq_step_n_noise(eq_fluid *h, int64_t n, const EqNoise *noise) {
+    NEED(h);
+    if (n < 0 || !noise) return eq_fail(EQ_ERR_INVALID, "bad step_n_noise arguments");
+    for (int64_t fr = 0; fr < n; ++fr) {
+        const uint64_t frame = noise->first_frame + (uint64_t)fr;
+        {
+            ProfScope ps(h, CAT_OTHER, 1);
+            EQ_LAUNCH(k_add_noise, 1, 32, 0, h->stream, h->f[EQ_F_VX], h->f[EQ_F_VY], (uint32_t)noise->seed,
+                      (uint32_t)(noise->seed >> 32), (uint32_t)frame, (uint32_t)(frame >> 32), noise->cos_t,
+                      noise->sin_t, noise->gain, h->L);
+            TRY(check_launch("k_add_noise"));
+        }
+        TRY(step_once(h));
+    }
+    return EQ_OK;
+}
+
 static void dump_lsx_stats(eq_fluid *h) {
     if (h->lsx_jobtimes && h->lsx_jobtimes_n) {
         std::vector<unsigned long long> v(h->lsx_jobtimes_n);
@@ -1296,6 +1314,20 @@ int eq_op_set_boundaries(eq_fluid *h, int orientation, int field) {
     TRY(f32_field(h, field, &x));
     if (!valid_orient(orientation)) return eq_fail(EQ_ERR_INVALID, "bad orientation");
     return set_boundaries(h, orientation, x);
+}
+
+// dense source field: x += scale * s on the whole grid (Stam's add_source; the reference only has point sources)
+int eq_op_add_source(eq_fluid *h, int x_field, int s_field, float scale) {
+    NEED(h);
+    float *x, *s;
+    TRY(f32_field(h, x_field, &x));
+    TRY(f32_field(h, s_field, &s));
+    if (x == s) return eq_fail(EQ_ERR_INVALID, "add_source needs two different fields");
+    const int quads = (h->L.N + 3) / 4;
+    dim3 grid((quads + 255) / 256, std::min(h->L.N, 148 * 8));
+    ProfScope ps(h, CAT_OTHER, 1);
+    EQ_LAUNCH(k_add_field, grid, 256, 0, h->stream, x, s, scale, h->L);
+    return check_launch("k_add_field");
 }
 
 int eq_op_lin_solve(eq_fluid *h, int orientation, int x_field, int x0_field, float a, float c, int64_t iters) {

@@ -434,6 +434,64 @@ __global__ void k_add_source(float *density, float *scratch, float *vx, float *v
     }
 }
 
+// ---- device-side add_noise (fluid.rs:575-599) ----------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11; the Random123 known-answer vectors are in tests/test_sources.py): counter =
+// (frame, 0), key = seed.  Integer work only, so host restatements agree bit for bit.
+__host__ __device__ __forceinline__ void eq_philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
+        c[0] = n0;
+        c[1] = (uint32_t)p1;
+        c[2] = n2;
+        c[3] = (uint32_t)p0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+}
+
+// One frame's impulse: a uniformly random grid point (:584-585) rotated about the centre (:587-593, the rotation of
+// geo's rotate_around_point: x' = cos*(x-cx) - sin*(y-cy) + cx) and added, times `gain` (2.0, :595-596), to the velocity
+// of the centre cell.  cos/sin come from the host: the angle depends on delta_t only (:578-583).
+__global__ void k_add_noise(float *vx, float *vy, uint32_t seed_lo, uint32_t seed_hi, uint32_t frame_lo, uint32_t frame_hi,
+                            float cos_t, float sin_t, float gain, EqLayout L) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    uint32_t c[4] = {frame_lo, frame_hi, 0u, 0u};
+    eq_philox4x32_10(c, seed_lo, seed_hi);
+    const uint32_t N = (uint32_t)L.N;
+    const uint32_t rx = (uint32_t)(((uint64_t)c[0] * N) >> 32), ry = (uint32_t)(((uint64_t)c[1] * N) >> 32);   // [0, N)
+    const float ctr = (float)(N / 2u);
+    const float dx = __fsub_rn((float)rx, ctr), dy = __fsub_rn((float)ry, ctr);
+    const float px = __fadd_rn(__fsub_rn(__fmul_rn(cos_t, dx), __fmul_rn(sin_t, dy)), ctr);
+    const float py = __fadd_rn(__fadd_rn(__fmul_rn(sin_t, dx), __fmul_rn(cos_t, dy)), ctr);
+    const size_t o = (size_t)(N / 2u) + (size_t)(N / 2u) * (size_t)L.P;
+    vx[o] = __fadd_rn(vx[o], __fmul_rn(px, gain));
+    vy[o] = __fadd_rn(vy[o], __fmul_rn(py, gain));
+}
+
+// Dense source field a la Stam's add_source: x[i,j] += scale * s[i,j] on every cell of the grid (one read of each, one
+// write: 12 B per cell).  One thread per float4 of a row; the pad columns beyond N are left alone.
+__global__ void k_add_field(float *__restrict__ x, const float *__restrict__ s, float scale, EqLayout L) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;               // float4 index within the row
+    const int N = L.N, i = q * 4;
+    if (i >= N) return;
+    for (int j = blockIdx.y; j < N; j += gridDim.y) {
+        const size_t o = (size_t)j * L.P + i;
+        if (i + 3 < N) {
+            float4 a = *reinterpret_cast<const float4 *>(x + o);
+            const float4 b = *reinterpret_cast<const float4 *>(s + o);
+            a.x = __fadd_rn(a.x, __fmul_rn(scale, b.x));
+            a.y = __fadd_rn(a.y, __fmul_rn(scale, b.y));
+            a.z = __fadd_rn(a.z, __fmul_rn(scale, b.z));
+            a.w = __fadd_rn(a.w, __fmul_rn(scale, b.w));
+            *reinterpret_cast<float4 *>(x + o) = a;
+        } else {
+            for (int e = 0; i + e < N; ++e) x[o + e] = __fadd_rn(x[o + e], __fmul_rn(scale, s[o + e]));
+        }
+    }
+}
+
 // field[x,y] += amount on [x0,x1) x [y0,y1)   (init_velocities :542-548, init_density :534-538)
 __global__ void k_add_rect(float *f, int x0, int y0, int x1, int y1, float amount, EqLayout L) {
     const int i = x0 + blockIdx.x * blockDim.x + threadIdx.x;

@@ -152,6 +152,27 @@ class Fluid:
         py = c + dx * math.sin(th) + dy * math.cos(th)
         return n // 2, n // 2, float(np.float32(px) * np.float32(2.0)), float(np.float32(py) * np.float32(2.0))
 
+    def noise_angle(self) -> float:
+        """The angle add_noise rotates by (fluid.rs:578-583): a function of delta_t only.  sin() stands in for
+        noise-0.7's Perlin::get([dt, dt]) (not vendored, see noise_impulse)."""
+        dt = float(self.simulation_configs.delta_t)
+        return float(np.float32(math.sin(12.9898 * dt + 78.233 * dt) * 6.28 * 2.0))
+
+    def device_noise(self, seed: int, first_frame: int = 0) -> "_lib.EqNoise":
+        """Parameters of the device-side add_noise: Philox4x32-10 keyed by `seed`, one counter per
+        frame; the rotation's cos/sin are evaluated once here (geo takes degrees), gain 2.0 (fluid.rs:595-596)."""
+        th = math.radians(self.noise_angle())
+        nz = _lib.EqNoise()
+        nz.seed, nz.first_frame = int(seed) & (2**64 - 1), int(first_frame)
+        nz.cos_t, nz.sin_t, nz.gain = math.cos(th), math.sin(th), 2.0
+        return nz
+
+    def step_n_noise(self, n: int, seed: int, first_frame: int = 0):
+        """n x { add_noise(); step() } (renderer_helpers.rs:54-60) with the impulses drawn on the device."""
+        self._push_params()
+        nz = self.device_noise(seed, first_frame)
+        _lib.check(self._lib, self._lib.eq_step_n_noise(self._h, int(n), C.byref(nz)))
+
     def add_noise(self):
         x, y, ax, ay = self.noise_impulse()
         self.add_velocity(x, y, ax, ay)
@@ -286,6 +307,10 @@ class Fluid:
     def op_project(self, vx, vy, p, div, iters):
         self._push_params()
         _lib.check(self._lib, self._lib.eq_op_project(self._h, self.FIELDS[vx], self.FIELDS[vy], self.FIELDS[p], self.FIELDS[div], iters))
+
+    def op_add_source(self, x, s, scale):
+        """x += scale * s over the whole grid (dense source field, Stam's add_source)."""
+        _lib.check(self._lib, self._lib.eq_op_add_source(self._h, self.FIELDS[x], self.FIELDS[s], scale))
 
     def op_advect(self, orientation, d, d0, vx, vy):
         self._push_params()

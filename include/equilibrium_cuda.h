@@ -92,6 +92,21 @@ typedef struct EqSource {
     float d_vx, d_vy, d_density;
 } EqSource;
 
+/* Device-side add_noise (fluid.rs:575-599).  Frame f of a call
+ * draws (rx, ry) in [0,size)^2 from Philox4x32-10(counter = first_frame + f,
+ * key = seed), rotates that point about the centre (size/2, size/2) with
+ * (cos_t, sin_t) and adds gain * rotated point to the centre cell's velocity
+ * (add_velocity, fluid.rs:127-131).  The reference's angle is a constant of
+ * delta_t (fluid.rs:578-583) and its gain is 2.0 (fluid.rs:595-596); its RNG is
+ * an unseeded thread_rng, so no sequence of it can be reproduced. */
+typedef struct EqNoise {
+    uint64_t seed;
+    uint64_t first_frame;
+    float cos_t, sin_t;
+    float gain;
+    float reserved;
+} EqNoise;
+
 /* Device-side time of each phase of the steps run since eq_profile_reset,
  * measured with CUDA events on the handle's stream (enable with
  * eq_profile_enable).  Times in ms, launches = kernel launches counted. */
@@ -144,6 +159,8 @@ int eq_step(eq_fluid *h);
  * by frame, frames counted from 0 for this call
  * (CurrentSimulation::simulate's loop, renderer_helpers.rs:54-66). */
 int eq_step_n(eq_fluid *h, int64_t n, const EqSource *sources, int64_t n_sources);
+/* n x { device-side add_noise; step() }: no source record crosses the bus. */
+int eq_step_n_noise(eq_fluid *h, int64_t n, const EqNoise *noise);
 /* wait for everything enqueued; returns EQ_ERR_TIMEOUT if a wavefront watchdog fired */
 int eq_sync(eq_fluid *h);
 
@@ -170,6 +187,9 @@ int eq_op_project(eq_fluid *h, int vx_field, int vy_field, int p_field, int div_
                   int64_t iters);                                                  /* fluid.rs:330-375 */
 int eq_op_advect(eq_fluid *h, int orientation, int d_field, int d0_field, int vx_field,
                  int vy_field);                                                    /* fluid.rs:378-432 */
+/* Dense source field: x += scale * s on every cell, as Stam's add_source does; the
+ * reference itself only has the point sources above (fluid.rs:120-131). */
+int eq_op_add_source(eq_fluid *h, int x_field, int s_field, float scale);
 
 /* ---- the caller's side of the frame loop -----------------------
  * After every step() the reference deep-copies the whole Fluid and sends it to the render

@@ -368,3 +368,41 @@ void ref_render_rgba(const float *density, const uint8_t *cells, uint32_t size, 
             }
         }
 }
+
+/* ---- device-side add_noise and dense sources ---------------------------
+ * Philox4x32-10, restated from the published algorithm (Salmon, Moraes, Dror, Shaw: "Parallel
+ * random numbers: as easy as 1, 2, 3", SC'11); pinned by the Random123 known-answer vectors in
+ * tests/test_sources.py. */
+void ref_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c0 = n0; c1 = (uint32_t)p1; c2 = n2; c3 = (uint32_t)p0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+/* The structure of add_noise (fluid.rs:575-599) with a seeded draw: random grid point (:584-585),
+ * rotated about the centre (:587-593; geo's rotate_around_point: x' = cos*(x-cx) - sin*(y-cy) + cx,
+ * y' = sin*(x-cx) + cos*(y-cy) + cy), times gain (:595-596).  xy = centre cell, a = impulse. */
+void ref_noise_impulse(uint64_t seed, uint64_t frame, uint32_t size, float cos_t, float sin_t, float gain,
+                       uint32_t xy[2], float a[2]) {
+    const uint32_t ctr[4] = {(uint32_t)frame, (uint32_t)(frame >> 32), 0u, 0u};
+    const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    uint32_t r[4];
+    ref_philox4x32_10(ctr, key, r);
+    const uint32_t rx = (uint32_t)(((uint64_t)r[0] * size) >> 32), ry = (uint32_t)(((uint64_t)r[1] * size) >> 32);
+    const float c = (float)(size / 2u);
+    const float dx = (float)rx - c, dy = (float)ry - c;
+    const float px = (cos_t * dx - sin_t * dy) + c;
+    const float py = (sin_t * dx + cos_t * dy) + c;
+    xy[0] = size / 2u; xy[1] = size / 2u;
+    a[0] = px * gain; a[1] = py * gain;
+}
+
+/* Stam's add_source on a whole field: x += scale * s */
+void ref_add_source(float *x, const float *s, float scale, size_t cells) {
+    for (size_t i = 0; i < cells; ++i) x[i] = x[i] + scale * s[i];
+}

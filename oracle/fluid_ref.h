@@ -22,6 +22,7 @@
 #ifndef EQ_ORACLE_FLUID_REF_H
 #define EQ_ORACLE_FLUID_REF_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -104,6 +105,12 @@ void ref_lin_solve_red_black(int orientation, float *x, const float *x0, float a
 void ref_render_rgba(const float *density, const uint8_t *cells, uint32_t size, uint32_t rows,
                      const uint8_t world[4], const uint8_t fluid[4], const uint8_t obstacle[4],
                      uint8_t *out);
+
+/* Device-side add_noise and dense sources (structure of fluid.rs:575-599). */
+void ref_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+void ref_noise_impulse(uint64_t seed, uint64_t frame, uint32_t size, float cos_t, float sin_t, float gain,
+                       uint32_t xy[2], float a[2]);
+void ref_add_source(float *x, const float *s, float scale, size_t cells);
 
 #ifdef __cplusplus
 }

@@ -61,6 +61,10 @@ def lib():
     L.ref_project.argtypes = [fp, fp, fp, fp, C.c_uint32, C.c_uint32, C.c_int64, u8p]
     L.ref_advect.argtypes = [C.c_int, fp, fp, fp, fp, C.c_uint32, C.c_uint32, C.c_float, u8p]
     L.ref_render_rgba.argtypes = [fp, u8p, C.c_uint32, C.c_uint32, u8p, u8p, u8p, u8p]
+    u32p = C.POINTER(C.c_uint32)
+    L.ref_philox4x32_10.argtypes = [u32p, u32p, u32p]
+    L.ref_noise_impulse.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_float, C.c_float, C.c_float, u32p, fp]
+    L.ref_add_source.argtypes = [fp, fp, C.c_float, C.c_size_t]
     _lib = L
     return L
 
@@ -165,3 +169,21 @@ def render_rgba(density, cells, world, fluid, obstacle) -> np.ndarray:
     lib().ref_render_rgba(_f(np.ascontiguousarray(density)), _u(np.ascontiguousarray(cells)), size, rows,
                           _u(cols[0]), _u(cols[1]), _u(cols[2]), _u(out.reshape(-1)))
     return out
+
+
+def philox4x32_10(ctr, key):
+    c, k, o = (C.c_uint32 * 4)(*ctr), (C.c_uint32 * 2)(*key), (C.c_uint32 * 4)()
+    lib().ref_philox4x32_10(c, k, o)
+    return list(o)
+
+
+def noise_impulse(seed, frame, size, cos_t, sin_t, gain=2.0):
+    """(x, y, ax, ay) of the seeded add_noise (structure of fluid.rs:575-599)."""
+    xy, a = (C.c_uint32 * 2)(), (C.c_float * 2)()
+    lib().ref_noise_impulse(seed, frame, size, cos_t, sin_t, gain, xy, a)
+    return int(xy[0]), int(xy[1]), float(a[0]), float(a[1])
+
+
+def add_source(x, s, scale):
+    assert x.flags.c_contiguous and s.flags.c_contiguous and x.shape == s.shape
+    lib().ref_add_source(_f(x), _f(s), scale, x.size)

@@ -245,3 +245,26 @@ class PyFluid:
         advect(PASSIVE, self.density, self.scratch_space, self.velocities_x, self.velocities_y,
                n, dt, w)
         self.scratch_space = self.density.copy()
+
+
+# ---- device-side add_noise: second, independent restatement ---------------------------------
+def philox4x32_10(ctr, key):
+    """Philox4x32-10 (Salmon et al., SC'11) on python ints."""
+    c, k = list(ctr), list(key)
+    for _ in range(10):
+        p0, p1 = 0xD2511F53 * c[0], 0xCD9E8D57 * c[2]
+        c = [(p1 >> 32) ^ c[1] ^ k[0], p1 & 0xFFFFFFFF, (p0 >> 32) ^ c[3] ^ k[1], p0 & 0xFFFFFFFF]
+        k = [(k[0] + 0x9E3779B9) & 0xFFFFFFFF, (k[1] + 0xBB67AE85) & 0xFFFFFFFF]
+    return c
+
+
+def noise_impulse(seed, frame, n, cos_t, sin_t, gain=2.0):
+    """Seeded add_noise (structure of fluid.rs:575-599) in numpy float32, every operation rounded separately."""
+    f = np.float32
+    r = philox4x32_10([frame & 0xFFFFFFFF, frame >> 32, 0, 0], [seed & 0xFFFFFFFF, seed >> 32])
+    rx, ry = (r[0] * n) >> 32, (r[1] * n) >> 32
+    c, cs, sn, g = f(n // 2), f(cos_t), f(sin_t), f(gain)
+    dx, dy = f(rx) - c, f(ry) - c
+    px = (cs * dx - sn * dy) + c
+    py = (sn * dx + cs * dy) + c
+    return n // 2, n // 2, float(px * g), float(py * g)

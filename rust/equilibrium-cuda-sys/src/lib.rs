@@ -34,6 +34,18 @@ pub struct EqSource {
     pub d_density: f32,
 }
 
+/// Device-side add_noise (fluid.rs:575-599): Philox4x32-10 keyed by `seed`, counter `first_frame + f`.
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct EqNoise {
+    pub seed: u64,
+    pub first_frame: u64,
+    pub cos_t: f32,
+    pub sin_t: f32,
+    pub gain: f32,
+    pub reserved: f32,
+}
+
 /// Colours of render_image (renderer_helpers.rs:122-143): r, g, b, a bytes.
 #[repr(C)]
 #[derive(Clone, Copy)]
@@ -75,6 +87,8 @@ extern "C" {
     pub fn eq_get_params(h: *mut eq_fluid, out: *mut EqParams) -> c_int;
     pub fn eq_step(h: *mut eq_fluid) -> c_int;
     pub fn eq_step_n(h: *mut eq_fluid, n: i64, sources: *const EqSource, n_sources: i64) -> c_int;
+    pub fn eq_step_n_noise(h: *mut eq_fluid, n: i64, noise: *const EqNoise) -> c_int;
+    pub fn eq_op_add_source(h: *mut eq_fluid, x_field: c_int, s_field: c_int, scale: f32) -> c_int;
     pub fn eq_sync(h: *mut eq_fluid) -> c_int;
     pub fn eq_upload(h: *mut eq_fluid, field: c_int, host: *const c_void, bytes: usize) -> c_int;
     pub fn eq_download(h: *mut eq_fluid, field: c_int, host: *mut c_void, bytes: usize) -> c_int;

@@ -41,6 +41,14 @@ impl CudaFluid {
     pub fn add_velocity(&mut self, x: u32, y: u32, ax: f32, ay: f32) {
         check(unsafe { sys::eq_add_velocity(self.h, x, y, ax, ay) });
     }
+    /// `n` x { add_noise(); step() } (renderer_helpers.rs:54-60) with the impulses drawn on the device: a seeded
+    /// Philox stream replaces the reference's unseeded thread_rng (fluid.rs:584-585).  `angle_deg` is what
+    /// add_noise passes to rotate_around_point (fluid.rs:578-583, a constant of delta_t).
+    pub fn step_n_noise(&mut self, n: i64, seed: u64, first_frame: u64, angle_deg: f32) {
+        let th = (angle_deg as f64).to_radians();
+        let nz = sys::EqNoise { seed, first_frame, cos_t: th.cos() as f32, sin_t: th.sin() as f32, gain: 2.0, reserved: 0.0 };
+        check(unsafe { sys::eq_step_n_noise(self.h, n, &nz) });
+    }
     /// fill_obstacle (fluid.rs:610-619) for the two approximate points of a Rectangle
     pub fn fill_rect(&mut self, p0: (i64, i64), p1: (i64, i64)) {
         check(unsafe { sys::eq_fill_rect(self.h, p0.0, p0.1, p1.0, p1.1) });

@@ -212,3 +212,35 @@ def check_golden_render(lib_path):
     px = dev.render_rgba(tuple(rec["obstacle"]))
     assert hashlib.sha256(np.ascontiguousarray(px).tobytes()).hexdigest() == rec["sha256"]
     assert int((px == np.array(rec["obstacle"], dtype=np.uint8)).all(axis=2).sum()) == rec["obstacle_pixels"] == 1408
+
+
+def check_device_noise(oracle, lib_path, n, k, frames_to_run, rects, seed, first_frame=0):
+    """n x { device-side add_noise; step } against the oracle fed its own restatement of the
+    impulse through add_velocity (fluid.rs:575-599 -> :127-131)."""
+    dev, ref = make_pair(oracle, lib_path, n, k, rects)
+    nz = dev.device_noise(seed, first_frame)
+    dev.step_n_noise(frames_to_run, seed, first_frame)
+    for fr in range(frames_to_run):
+        x, y, ax, ay = oracle.noise_impulse(seed, first_frame + fr, n, nz.cos_t, nz.sin_t, nz.gain)
+        assert (x, y) == (n // 2, n // 2) and abs(ax) <= 4 * n and abs(ay) <= 4 * n
+        ref.add_velocity(x, y, ax, ay)
+        ref.step()
+    dev.sync()
+    assert_state_equal(dev, ref, f"device noise N={n} K={k} frames={frames_to_run} seed={seed}")
+    dev.close()
+
+
+def check_add_source(oracle, lib_path, n, scale=0.02, seed=0):
+    rng = np.random.default_rng(seed)
+    dev, _ = make_pair(oracle, lib_path, n, 1)
+    x, s = rnd(rng, n), rnd(rng, n, 5.0)
+    other = rnd(rng, n)
+    dev.upload("velocities_x", x)
+    dev.upload("velocities_x0", s)
+    dev.upload("velocities_y", other)
+    dev.op_add_source("velocities_x", "velocities_x0", scale)
+    oracle.add_source(x, s, scale)
+    got = dev.download("velocities_x")
+    assert bits_equal(got, x), f"add_source N={n}: {describe_diff(got, x)}"
+    assert bits_equal(dev.download("velocities_x0"), s) and bits_equal(dev.download("velocities_y"), other)
+    dev.close()
