@@ -36,6 +36,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
+    # not a BASELINE config: small enough for the emulated build, so the CPU tests can run this arm's whole flow
+    "tiny": dict(size=64, k=2, rects=1, seed=64, cpu_rows=64),
     "c2": dict(size=1024, k=20, rects=0, seed=1024, cpu_rows=1024),
     "c3": dict(size=4096, k=40, rects=64, seed=4096, cpu_rows=512),
     "c4": dict(size=16384, k=20, rects=16, seed=16384, cpu_rows=512),

@@ -1,5 +1,7 @@
 """bench.py's JSON contract, as far as it can be checked without a GPU: the reference arm (the CPU oracle port timed on
-the host) prints one line with the keys the driver reads."""
+the host) prints one line with the keys the driver reads, and the product arm runs its whole flow (device-resident
+timing, per-phase profile, e2e frame loop with snapshots, full mirror, red-black leg, CPU baseline) on the emulated
+build of the product sources with a workload small enough for it."""
 import json
 import os
 import subprocess
@@ -30,3 +32,30 @@ def test_reference_arm_is_silent_on_other_ranks(oracle):
                           "--gpus", "2", "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=120,
                          cwd=ROOT, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_product_arm_flow_on_the_emulated_build(oracle, emu_lib):
+    env = dict(os.environ, EQUILIBRIUM_CUDA_LIB=emu_lib, EQ_EMU_SMS="4")
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        env.pop(k, None)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", "tiny", "--steps", "1",
+                          "--warmup", "3"], capture_output=True, text=True, timeout=900, cwd=ROOT, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert "impl" not in d and d["metric"] == "grid cell-updates/sec per frame" and d["unit"] == "cell-updates/s"
+    assert d["n_gpus"] == 1 and d["steps"] == 1 and d["warmup"] >= 3 and d["value"] > 0 and d["dtype"] == "f32"
+    assert d["higher_is_better"] is True and d["scaling"] in ("weak", "strong") and d["vs_baseline"] is None
+    assert d["data"] == "synthetic" and "workload" in d["config"] and "model" not in d["config"]
+    assert abs(d["value"] - 64 * 64 * 1 / (d["ms_per_step"] * 1e-3)) <= 1e-6 * d["value"]
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and r["peak"] > 0 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
+    assert "traffic" in r and r["algorithmic_bytes_per_launch"] > 0
+    assert d["gpu_launches"] > 0 and set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    e = d["e2e"]
+    assert e["value"] > 0 and e["unit"] == d["unit"] and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] == 64 * 64 * 4
+    assert e["value"] != d["value"]
+    c = d["cpu_baseline"]
+    assert c["kind"] == "port" and c["cores"] == 1 and c["value"] > 0 and c["sample"] and c["unit"] == d["unit"]
+    assert d["red_black"]["value"] > 0 and d["red_black"]["roofline"]["bound"] == "hbm"
