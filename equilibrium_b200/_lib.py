@@ -95,6 +95,7 @@ SIGNATURES = {
     "eq_get_params": (C.c_int, [_H, C.POINTER(EqParams)]),
     "eq_step": (C.c_int, [_H]),
     "eq_step_n": (C.c_int, [_H, C.c_int64, C.POINTER(EqSource), C.c_int64]),
+    "eq_add_noise": (C.c_int, [_H, C.POINTER(EqNoise)]),
     "eq_step_n_noise": (C.c_int, [_H, C.c_int64, C.POINTER(EqNoise)]),
     "eq_sync": (C.c_int, [_H]),
     "eq_upload": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_size_t]),

@@ -1140,19 +1140,25 @@ int eq_step_n(eq_fluid *h, int64_t n, const EqSource *sources, int64_t n_sources
     return EQ_OK;
 }
 
-// add_noise on the device: frame f of this call gets the impulse of Philox counter first_frame + f
+// add_noise on the device: the impulse of Philox counter noise->first_frame
+int eq_add_noise(eq_fluid *h, const EqNoise *noise) {
+    NEED(h);
+    if (!noise) return eq_fail(EQ_ERR_INVALID, "null noise parameters");
+    const uint64_t frame = noise->first_frame;
+    ProfScope ps(h, CAT_OTHER, 1);
+    EQ_LAUNCH(k_add_noise, 1, 32, 0, h->stream, h->f[EQ_F_VX], h->f[EQ_F_VY], (uint32_t)noise->seed,
+              (uint32_t)(noise->seed >> 32), (uint32_t)frame, (uint32_t)(frame >> 32), noise->cos_t, noise->sin_t,
+              noise->gain, h->L);
+    return check_launch("k_add_noise");
+}
+
+// n x { add_noise; step }: frame f of this call gets the impulse of Philox counter first_frame + f
 int eq_step_n_noise(eq_fluid *h, int64_t n, const EqNoise *noise) {
     NEED(h);
     if (n < 0 || !noise) return eq_fail(EQ_ERR_INVALID, "bad step_n_noise arguments");
-    for (int64_t fr = 0; fr < n; ++fr) {
-        const uint64_t frame = noise->first_frame + (uint64_t)fr;
-        {
-            ProfScope ps(h, CAT_OTHER, 1);
-            EQ_LAUNCH(k_add_noise, 1, 32, 0, h->stream, h->f[EQ_F_VX], h->f[EQ_F_VY], (uint32_t)noise->seed,
-                      (uint32_t)(noise->seed >> 32), (uint32_t)frame, (uint32_t)(frame >> 32), noise->cos_t,
-                      noise->sin_t, noise->gain, h->L);
-            TRY(check_launch("k_add_noise"));
-        }
+    EqNoise nz = *noise;
+    for (int64_t fr = 0; fr < n; ++fr, ++nz.first_frame) {
+        TRY(eq_add_noise(h, &nz));
         TRY(step_once(h));
     }
     return EQ_OK;

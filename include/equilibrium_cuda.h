@@ -159,6 +159,8 @@ int eq_step(eq_fluid *h);
  * by frame, frames counted from 0 for this call
  * (CurrentSimulation::simulate's loop, renderer_helpers.rs:54-66). */
 int eq_step_n(eq_fluid *h, int64_t n, const EqSource *sources, int64_t n_sources);
+/* add_noise (fluid.rs:575-599) on the device: the impulse of counter noise->first_frame, no step. */
+int eq_add_noise(eq_fluid *h, const EqNoise *noise);
 /* n x { device-side add_noise; step() }: no source record crosses the bus. */
 int eq_step_n_noise(eq_fluid *h, int64_t n, const EqNoise *noise);
 /* wait for everything enqueued; returns EQ_ERR_TIMEOUT if a wavefront watchdog fired */

@@ -87,6 +87,7 @@ extern "C" {
     pub fn eq_get_params(h: *mut eq_fluid, out: *mut EqParams) -> c_int;
     pub fn eq_step(h: *mut eq_fluid) -> c_int;
     pub fn eq_step_n(h: *mut eq_fluid, n: i64, sources: *const EqSource, n_sources: i64) -> c_int;
+    pub fn eq_add_noise(h: *mut eq_fluid, noise: *const EqNoise) -> c_int;
     pub fn eq_step_n_noise(h: *mut eq_fluid, n: i64, noise: *const EqNoise) -> c_int;
     pub fn eq_op_add_source(h: *mut eq_fluid, x_field: c_int, s_field: c_int, scale: f32) -> c_int;
     pub fn eq_sync(h: *mut eq_fluid) -> c_int;
