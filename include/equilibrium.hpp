@@ -278,5 +278,89 @@ private:
     uint64_t noise_frame_ = 0;
 };
 
+// A frame buffer in pinned host memory (eq_host_alloc) for the snapshot path
+class PinnedFrame {
+public:
+    explicit PinnedFrame(size_t bytes) : bytes_(bytes) { check(eq_host_alloc(&p_, bytes)); }
+    PinnedFrame(const PinnedFrame &) = delete;
+    PinnedFrame &operator=(const PinnedFrame &) = delete;
+    PinnedFrame(PinnedFrame &&o) noexcept : p_(o.p_), bytes_(o.bytes_) { o.p_ = nullptr; }
+    ~PinnedFrame() {
+        if (p_) eq_host_free(p_);
+    }
+    void *data() { return p_; }
+    const void *data() const { return p_; }
+    size_t bytes() const { return bytes_; }
+
+private:
+    void *p_ = nullptr;
+    size_t bytes_ = 0;
+};
+
+// FluidStep (renderer_helpers.rs:21-24): what simulate() sends to the render thread
+struct FluidStep {
+    Fluid fluid;
+    int64_t frame_number;
+};
+// what the snapshot path sends instead: the one array the render thread consumes (renderer_helpers.rs:145-167), valid
+// until the callback returns
+struct FrameView {
+    const void *data;       // size*size f32 density (EQ_SNAP_DENSITY) or size*size RGBA pixels (EQ_SNAP_RGBA)
+    size_t bytes;
+    int64_t frame_number;
+};
+
+// CurrentSimulation (renderer_helpers.rs:29-81)
+class CurrentSimulation {
+public:
+    Fluid fluid;
+    std::vector<ObstaclesType> obstacles;
+
+    // Default (renderer_helpers.rs:39-48): Fluid::default() and the default rectangle
+    CurrentSimulation() : fluid(), obstacles{Rectangle()} {}
+    CurrentSimulation(Fluid f, std::vector<ObstaclesType> obs) : fluid(std::move(f)), obstacles(std::move(obs)) {}
+
+    // simulate (renderer_helpers.rs:52-72) as the reference does it: a deep copy of the Fluid per frame goes to `tx`
+    template <class Tx>
+    void simulate(Tx &&tx) {
+        mark_fluid_obstacles();
+        for (int64_t i = 0; i < fluid.simulation_configs.frames; ++i) {
+            if (fluid.fluid_configs.has_perlin_noise) fluid.add_noise();
+            fluid.step();
+            tx(FluidStep{fluid.clone(), i});
+        }
+    }
+    // The same loop over the snapshot path: frame i's array travels to a pinned buffer on the copy
+    // stream while step i+1 runs; `tx` gets the frames in order, each as soon as it has landed.
+    template <class Tx>
+    void simulate_frames(int kind, Tx &&tx, Color32 obstacles_color = RED) {
+        mark_fluid_obstacles();
+        const size_t bytes = fluid.cells() * 4;      // f32 density and RGBA pixels are both 4 bytes per cell
+        PinnedFrame buf[2] = {PinnedFrame(bytes), PinnedFrame(bytes)};
+        const int64_t frames = fluid.simulation_configs.frames;
+        for (int64_t i = 0; i < frames; ++i) {
+            if (fluid.fluid_configs.has_perlin_noise) fluid.add_noise();
+            fluid.step();
+            const int slot = static_cast<int>(i & 1);
+            fluid.snapshot_begin(kind, slot, buf[slot].data(), bytes, obstacles_color);
+            if (i > 0) {
+                fluid.snapshot_wait(1 - slot);       // frame i-1 has landed
+                tx(FrameView{buf[1 - slot].data(), bytes, i - 1});
+            }
+        }
+        if (frames > 0) {
+            const int last = static_cast<int>((frames - 1) & 1);
+            fluid.snapshot_wait(last);
+            tx(FrameView{buf[last].data(), bytes, frames - 1});
+        }
+    }
+
+private:
+    // mark_fluid_obstacles (renderer_helpers.rs:76-80)
+    void mark_fluid_obstacles() {
+        for (ObstaclesType &o : obstacles) fluid.fill_obstacle(o);
+    }
+};
+
 }  // namespace equilibrium
 #endif

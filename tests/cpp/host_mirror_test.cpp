@@ -1,6 +1,7 @@
 // TEST INFRASTRUCTURE.  Drives the C++ host mirror (include/equilibrium.hpp) the way the reference's own callers and
 // tests drive `Fluid`, and compares with the CPU oracle (oracle/fluid_ref.h) bit for bit.  Linked against either the real
 // CUDA library (pytest -m gpu) or the emulated build of the same sources (CPU tests); tests/test_cpp_host.py builds it.
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <random>
@@ -56,7 +57,7 @@ static void compare(Fluid &dev, ref_fluid *ref, const char *where) {
 static void default_scene_frames() {
     FluidConfigs fc;
     SimulationConfigs sc;                        // 0.02, 16, 128  (configs.rs:14-22)
-    sc.frames = 6;                               // frames is also the GS iteration count (fluid.rs:445)
+    sc.frames = 2;                               // frames is also the GS iteration count (fluid.rs:445)
     Fluid fluid = Fluid::new_(fc, sc);
     ref_fluid *ref = ref_fluid_new(sc.size, sc.size, sc.delta_t, sc.frames, 0, fc.diffusion, fc.viscousity);
     Rectangle rect;                              // (80,80)-(110,110)  (obstacle.rs:47-51)
@@ -65,7 +66,7 @@ static void default_scene_frames() {
     compare(fluid, ref, "after construction");
     std::mt19937 rng(0);
     std::uniform_real_distribution<float> u(-256.f, 256.f);
-    for (int64_t i = 0; i < 4; ++i) {
+    for (int64_t i = 0; i < 2; ++i) {
         const float ax = u(rng), ay = u(rng);
         fluid.add_velocity(sc.size / 2, sc.size / 2, ax, ay);
         ref_add_velocity(ref, sc.size / 2, sc.size / 2, ax, ay);
@@ -74,7 +75,7 @@ static void default_scene_frames() {
         Fluid copy = fluid.clone();              // what the reference sends to the render thread every frame (:61-65)
         compare(copy, ref, "clone of a frame");
     }
-    compare(fluid, ref, "default scene, 4 frames");
+    compare(fluid, ref, "default scene, 2 frames");
 
     // the pub config structs are live (the GUI edits them between runs)
     fluid.simulation_configs.delta_t = 0.05f;
@@ -193,18 +194,80 @@ static void error_behaviour() {
     fluid.sync();
 }
 
+// CurrentSimulation::simulate (renderer_helpers.rs:52-72): per-frame clones, then the same run over the snapshot path
+static void current_simulation() {
+    SimulationConfigs sc(0.02f, 3, 64);   // small: this also runs on the host emulator
+    DeviceOptions opt;
+    opt.noise_seed = 77;
+    auto make_ref = [&]() {
+        ref_fluid *r = ref_fluid_new(64, 64, 0.02f, 3, 0, 0.0f, 0.001f);
+        ref_fill_rect(r, 20, 24, 40, 44);
+        return r;
+    };
+    auto ref_frame = [&](ref_fluid *r, const Fluid &f, uint64_t fr) {
+        const EqNoise nz = f.device_noise(fr);
+        uint32_t xy[2];
+        float a[2];
+        ref_noise_impulse(nz.seed, fr, 64, nz.cos_t, nz.sin_t, nz.gain, xy, a);
+        ref_add_velocity(r, xy[0], xy[1], a[0], a[1]);
+        ref_fluid_step(r);
+    };
+    {   // the reference's way: a FluidStep with a deep copy per frame
+        CurrentSimulation sim(Fluid::new_(FluidConfigs(), sc, opt), {Rectangle({20, 24}, {40, 44}, 64)});
+        ref_fluid *ref = make_ref();
+        int64_t seen = 0;
+        sim.simulate([&](FluidStep step) {
+            EXPECT(step.frame_number == seen, "frame order");
+            ref_frame(ref, sim.fluid, static_cast<uint64_t>(seen));
+            compare(step.fluid, ref, "FluidStep clone");
+            ++seen;
+        });
+        EXPECT(seen == 3, "3 frames sent, got %lld", (long long)seen);
+        ref_fluid_free(ref);
+    }
+    for (int kind : {EQ_SNAP_DENSITY, EQ_SNAP_RGBA}) {   // the snapshot path: one array per frame, overlapped
+        CurrentSimulation sim(Fluid::new_(FluidConfigs(), sc, opt), {Rectangle({20, 24}, {40, 44}, 64)});
+        ref_fluid *ref = make_ref();
+        int64_t seen = 0;
+        const FluidConfigs fc;
+        std::vector<uint8_t> want(64 * 64 * 4);
+        sim.simulate_frames(kind, [&](FrameView fv) {
+            EXPECT(fv.frame_number == seen && fv.bytes == want.size(), "frame order / size");
+            ref_frame(ref, sim.fluid, static_cast<uint64_t>(seen));
+            const float *rd = static_cast<const float *>(ref_fluid_field(ref, REF_F_DENSITY));
+            if (kind == EQ_SNAP_DENSITY) {
+                std::memcpy(want.data(), rd, want.size());
+            } else {
+                const uint8_t world[4] = {fc.world_color.r, fc.world_color.g, fc.world_color.b, fc.world_color.a};
+                const uint8_t fl[4] = {fc.fluid_color.r, fc.fluid_color.g, fc.fluid_color.b, fc.fluid_color.a};
+                const uint8_t obs[4] = {255, 0, 0, 255};
+                ref_render_rgba(rd, static_cast<const uint8_t *>(ref_fluid_field(ref, REF_F_CELLS)), 64, 64, world, fl, obs, want.data());
+            }
+            EXPECT(std::memcmp(fv.data, want.data(), want.size()) == 0, "snapshot kind %d frame %lld differs", kind, (long long)seen);
+            ++seen;
+        });
+        EXPECT(seen == 3, "3 frames delivered, got %lld", (long long)seen);
+        ref_fluid_free(ref);
+    }
+    CurrentSimulation def;   // Default: Fluid::default() + the default rectangle
+    EXPECT(def.obstacles.size() == 1 && def.fluid.simulation_configs.frames == 16, "CurrentSimulation::default");
+}
+
 int main() {
     if (eq_device_count() < 1) {
         std::printf("no CUDA device: the product path has no CPU fallback\n");
         return 2;
     }
-    reference_unit_tests();
-    default_scene_obstacle_pixels();
-    default_double_init();
-    default_scene_frames();
-    edited_rectangle_clamps();
-    device_noise();
-    error_behaviour();
+    struct { const char *name; void (*fn)(); } sections[] = {
+        {"reference_unit_tests", reference_unit_tests}, {"default_scene_obstacle_pixels", default_scene_obstacle_pixels},
+        {"default_double_init", default_double_init},   {"default_scene_frames", default_scene_frames},
+        {"edited_rectangle_clamps", edited_rectangle_clamps}, {"device_noise", device_noise},
+        {"error_behaviour", error_behaviour},           {"current_simulation", current_simulation}};
+    for (auto &sec : sections) {
+        const auto t0 = std::chrono::steady_clock::now();
+        sec.fn();
+        std::printf("%-32s %.2f s\n", sec.name, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+    }
     if (failures) std::printf("%d FAILED\n", failures);
     else std::printf("host mirror ok\n");
     return failures ? 1 : 0;
