@@ -1,4 +1,4 @@
-"""Regenerates tests/golden/default_scene.json and default_scene_density_f16.npy.
+"""Regenerates tests/golden/default_scene.json, default_scene_density_f16.npy, render_rgba.json and device_noise.json.
 
 The reference is Rust and cannot be built or imported in the build image, and
 its own tests pin no output of step(), so these vectors come from
@@ -96,10 +96,53 @@ def render_golden():
     print("written", os.path.join(HERE, "render_rgba.json"))
 
 
+def noise_golden():
+    """Device-side add_noise: impulses and states of a seeded run, written only after the C and the
+    numpy restatements of Philox4x32-10 + the impulse arithmetic + step() agree bit for bit."""
+    import math
+    n, k, frames, seed, first = 64, 4, 6, 0x5EED0FEED, 2**32 - 2      # the counter crosses 2^32 inside the run
+    dt = 0.02
+    angle = float(np.float32(math.sin(12.9898 * dt + 78.233 * dt) * 6.28 * 2.0))    # Fluid.noise_angle()
+    cs, sn = float(np.float32(math.cos(math.radians(angle)))), float(np.float32(math.sin(math.radians(angle))))
+    rects = [(10, 20, 30, 40)]
+    c, p = O.RefFluid(n, dt, k), P.PyFluid(n, dt, k)
+    for r in rects:
+        c.fill_rect(*r)
+        p.fill_rect(*r)
+    imps, states = [], {}
+    for fr in range(frames):
+        a = O.noise_impulse(seed, first + fr, n, cs, sn, 2.0)
+        b = P.noise_impulse(seed, first + fr, n, cs, sn, 2.0)
+        assert a[:2] == b[:2] and np.float32(a[2]).tobytes() == np.float32(b[2]).tobytes() \
+            and np.float32(a[3]).tobytes() == np.float32(b[3]).tobytes(), (fr, a, b)
+        imps.append([a[0], a[1], float(a[2]).hex(), float(a[3]).hex()])
+        c.add_velocity(*a)
+        p.add_velocity(*a)
+        c.step()
+        p.step()
+        if fr + 1 in (1, frames):
+            rec = {}
+            for name, fid, pname in FIELDS:
+                x, y = c.field(fid), getattr(p, pname).reshape(n, n)
+                assert np.array_equal(x.view(np.uint32), y.view(np.uint32)), (name, fr)
+                rec[name] = sha(x)
+            states[str(fr + 1)] = rec
+    rec = {"note": "oracle-generated (C and numpy restatements agree); the reference's add_noise is unseeded and cannot "
+                   "be reproduced, see SURVEY.md 8a row a12", "n": n, "k": k, "rects": rects, "seed": seed,
+           "first_frame": first, "delta_t": dt, "angle_deg": float(angle).hex(), "cos_t": float(cs).hex(),
+           "sin_t": float(sn).hex(), "gain": 2.0, "impulses": imps, "frames": states}
+    with open(os.path.join(HERE, "device_noise.json"), "w") as f:
+        json.dump(rec, f, indent=1, sort_keys=True)
+    print("written", os.path.join(HERE, "device_noise.json"))
+
+
 def main():
     render_only = "--render-only" in sys.argv
     if render_only:
         render_golden()
+        return
+    if "--noise-only" in sys.argv:
+        noise_golden()
         return
     gold = {"note": "oracle-generated (both restatements agree); not reference outputs",
             "scenes": {}}
@@ -118,6 +161,7 @@ def main():
         json.dump(gold, f, indent=1, sort_keys=True)
     print("written", os.path.join(HERE, "default_scene.json"))
     render_golden()
+    noise_golden()
 
 
 if __name__ == "__main__":

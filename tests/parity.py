@@ -244,3 +244,30 @@ def check_add_source(oracle, lib_path, n, scale=0.02, seed=0):
     assert bits_equal(got, x), f"add_source N={n}: {describe_diff(got, x)}"
     assert bits_equal(dev.download("velocities_x0"), s) and bits_equal(dev.download("velocities_y"), other)
     dev.close()
+
+
+def check_golden_device_noise(lib_path):
+    """tests/golden/device_noise.json with no oracle in the loop: a seeded run whose Philox counter crosses 2^32."""
+    import hashlib
+    import json
+    import os
+    import ctypes as C
+    from equilibrium_b200 import _lib
+    with open(os.path.join(os.path.dirname(__file__), "golden", "device_noise.json")) as f:
+        g = json.load(f)
+    n, k = g["n"], g["k"]
+    dev = Fluid(FluidConfigs(), SimulationConfigs(g["delta_t"], k, n), lib_path=lib_path)
+    for r in g["rects"]:
+        dev.fill_obstacle(Rectangle((r[0], r[1]), (r[2], r[3]), n))
+    # the mirror derives the same rotation from delta_t as the generator did
+    nz = dev.device_noise(g["seed"], g["first_frame"])
+    assert float(nz.cos_t).hex() == g["cos_t"] and float(nz.sin_t).hex() == g["sin_t"] and nz.gain == g["gain"]
+    done = 0
+    for upto in sorted(int(s) for s in g["frames"]):
+        nz.first_frame = g["first_frame"] + done
+        _lib.check(dev._lib, dev._lib.eq_step_n_noise(dev._h, upto - done, C.byref(nz)))
+        done = upto
+        for name, _ in F32_FIELDS:
+            got = hashlib.sha256(np.ascontiguousarray(dev.download(name)).tobytes()).hexdigest()
+            assert got == g["frames"][str(upto)][name], (upto, name)
+    dev.close()

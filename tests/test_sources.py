@@ -89,3 +89,24 @@ def test_device_noise_gpu(oracle, cuda_lib, n, k, frames, seed, first):
 @pytest.mark.parametrize("n", [128, 1001, 4096])
 def test_add_source_gpu(oracle, cuda_lib, n):
     P.check_add_source(oracle, cuda_lib, n)
+
+
+def test_oracle_matches_golden_noise_impulses(oracle):
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "device_noise.json")) as f:
+        g = json.load(f)
+    cs, sn = float.fromhex(g["cos_t"]), float.fromhex(g["sin_t"])
+    for fr, (x, y, ax, ay) in enumerate(g["impulses"]):
+        for impl in (oracle.noise_impulse, pyref.noise_impulse):
+            got = impl(g["seed"], g["first_frame"] + fr, g["n"], cs, sn, g["gain"])
+            assert got == (x, y, float.fromhex(ax), float.fromhex(ay)), (fr, impl.__module__)
+
+
+def test_golden_device_noise_emulated(emu_lib):
+    P.check_golden_device_noise(emu_lib)
+
+
+@pytest.mark.gpu
+def test_golden_device_noise_gpu(cuda_lib):
+    P.check_golden_device_noise(cuda_lib)
