@@ -6,6 +6,7 @@ from .configs import FluidConfigs, SimulationConfigs
 from .fluid import ContainerWall, Fluid, connect_distributed, connect_local
 from .obstacle import ObstaclesType, Rectangle
 from ._lib import EquilibriumError
+from .simulation import CurrentSimulation, FluidStep
 
 __all__ = ["Fluid", "FluidConfigs", "SimulationConfigs", "Rectangle", "ObstaclesType",
-           "ContainerWall", "EquilibriumError", "connect_local", "connect_distributed"]
+           "ContainerWall", "EquilibriumError", "CurrentSimulation", "FluidStep", "connect_local", "connect_distributed"]

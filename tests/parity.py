@@ -271,3 +271,53 @@ def check_golden_device_noise(lib_path):
             got = hashlib.sha256(np.ascontiguousarray(dev.download(name)).tobytes()).hexdigest()
             assert got == g["frames"][str(upto)][name], (upto, name)
     dev.close()
+
+
+def check_current_simulation(oracle, lib_path, n=64, k=3, rect=(20, 24, 40, 44), seed=5):
+    """CurrentSimulation (renderer_helpers.rs:29-81): the reference's clone-per-frame loop, then the same run over the
+    snapshot path (f32 density, then RGBA), each frame compared with the oracle."""
+    from equilibrium_b200 import CurrentSimulation
+
+    def make():
+        f = Fluid(FluidConfigs(), SimulationConfigs(0.02, k, n), lib_path=lib_path, noise_seed=seed)
+        twin = Fluid(FluidConfigs(), SimulationConfigs(0.02, k, n), lib_path=lib_path, noise_seed=seed)   # same host RNG
+        ref = oracle.RefFluid(n, 0.02, k)
+        ref.fill_rect(*rect)
+        return CurrentSimulation(f, [Rectangle(rect[:2], rect[2:], n)]), twin, ref
+
+    def ref_frame(twin, ref):
+        ref.add_velocity(*twin.noise_impulse())
+        ref.step()
+
+    sim, twin, ref = make()
+    seen = []
+
+    def on_step(step):
+        assert step.frame_number == len(seen)
+        ref_frame(twin, ref)
+        assert_state_equal(step.fluid, ref, f"FluidStep {step.frame_number}")
+        seen.append(step.frame_number)
+        step.fluid.close()
+
+    sim.simulate(on_step)
+    assert seen == list(range(k))
+
+    for rgba in (False, True):
+        sim, twin, ref = make()
+        seen = []
+        world, fluid = sim.fluid.fluid_configs.world_color, sim.fluid.fluid_configs.fluid_color
+
+        def on_frame(i, arr):
+            assert i == len(seen)
+            ref_frame(twin, ref)
+            if rgba:
+                assert np.array_equal(arr, oracle.render_rgba(ref.density, ref.cells, world, fluid, (255, 0, 0, 255))), i
+            else:
+                assert bits_equal(arr, ref.density), f"frame {i}: {describe_diff(arr, ref.density)}"
+            seen.append(i)
+
+        sim.simulate_frames(on_frame, rgba=rgba)
+        assert seen == list(range(k))
+    # Default: Fluid::default() + the default rectangle, and has_perlin_noise = false skips add_noise
+    sim = CurrentSimulation(lib_path=lib_path)
+    assert len(sim.obstacles) == 1 and sim.fluid.simulation_configs.frames == 16

@@ -162,3 +162,7 @@ def test_render_rgba_and_snapshots(oracle, emu_lib, n, steps):
 
 def test_render_rgba_golden_pixels(emu_lib):
     P.check_golden_render(emu_lib)
+
+
+def test_current_simulation_loop(oracle, emu_lib):
+    P.check_current_simulation(oracle, emu_lib)
