@@ -138,3 +138,26 @@ def test_unattached_handle_refuses_to_step(emu_lib):
     f = Fluid(FluidConfigs(), SimulationConfigs(0.02, 1, 96), lib_path=emu_lib, rank=0, world=2)
     with pytest.raises(EquilibriumError):
         f.step()
+
+
+def test_device_noise_across_two_slabs(oracle, emu_lib):
+    # every rank draws the same Philox impulse for the centre cell; only the owner's copy of that row is authoritative
+    world, n, k, seed = 2, 96, 2, 99
+    rects = [(20, 28, 40, 40)]
+    fluids = make_rank_fluids(emu_lib, world, n, k, rects)
+    ref = oracle.RefFluid(n, 0.02, k)
+    for r in rects:
+        ref.fill_rect(*r)
+    nz = fluids[0].device_noise(seed)
+
+    def body(r, barrier):
+        fluids[r].step_n_noise(2, seed)
+        fluids[r].sync()
+
+    for fr in range(2):
+        ref.add_velocity(*oracle.noise_impulse(seed, fr, n, nz.cos_t, nz.sin_t, nz.gain))
+        ref.step()
+    run_ranks(world, body)
+    for name, fid in P.F32_FIELDS:
+        got, want = assemble(fluids, name), ref.field(fid)
+        assert P.bits_equal(got, want), f"{name}: {P.describe_diff(got, want)}"
