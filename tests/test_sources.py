@@ -49,21 +49,10 @@ def test_noise_points_cover_the_grid(oracle):
     assert oracle.noise_impulse(7, 0, n, 1.0, 0.0, 1.0) != oracle.noise_impulse(8, 0, n, 1.0, 0.0, 1.0)
 
 
-@pytest.mark.parametrize("n,k,frames,seed,first", [(64, 3, 4, 1, 0), (97, 2, 3, 0xDEADBEEFCAFE, 2**33 + 5)])
+# (the golden run below also cuts one stream into two calls)
+@pytest.mark.parametrize("n,k,frames,seed,first", [(97, 2, 3, 0xDEADBEEFCAFE, 2**33 + 5)])
 def test_device_noise_emulated(oracle, emu_lib, n, k, frames, seed, first):
     P.check_device_noise(oracle, emu_lib, n, k, frames, [(10, 12, 30, 20)], seed, first)
-
-
-def test_device_noise_continues_a_stream(oracle, emu_lib):
-    # 2 + 3 frames with first_frame advanced == 5 frames in one call
-    n, k = 64, 2
-    a = Fluid(FluidConfigs(), SimulationConfigs(0.02, k, n), lib_path=emu_lib)
-    b = Fluid(FluidConfigs(), SimulationConfigs(0.02, k, n), lib_path=emu_lib)
-    a.step_n_noise(5, 42)
-    b.step_n_noise(2, 42)
-    b.step_n_noise(3, 42, first_frame=2)
-    for name, _ in P.F32_FIELDS:
-        assert P.bits_equal(a.download(name), b.download(name)), name
 
 
 @pytest.mark.parametrize("n", [64, 97, 130])
