@@ -76,14 +76,34 @@ void launch(const char *name, dim3 grid, dim3 block, size_t smem, const std::fun
         return;
     }
     if (mode == BLOCK_THREADS) {
-        for (unsigned bz = 0; bz < grid.z; ++bz)
-            for (unsigned by = 0; by < grid.y; ++by)
-                for (unsigned bx = 0; bx < grid.x; ++bx) {
-                    auto bs = make_block(block, smem);
-                    std::vector<std::thread> pool;
-                    run_block_threads(*bs, grid, block, uint3_emu{bx, by, bz}, body, pool);
-                    for (auto &t : pool) t.join();
+        // one CTA at a time, its threads real OS threads.  The threads are created once per launch and walk the CTAs
+        // together: after a CTA every thread arrives at `next_block`, whose completion step installs a fresh
+        // BlockState (zeroed shared memory, new barriers) for the following one.
+        const int nthreads = (int)(block.x * block.y * block.z);
+        const unsigned nblocks = grid.x * grid.y * grid.z;
+        if (nblocks == 0 || nthreads == 0) return;
+        std::unique_ptr<BlockState> bs = make_block(block, smem);
+        auto renew = [&]() noexcept { bs = make_block(block, smem); };
+        std::barrier<decltype(renew)> next_block(nthreads, renew);
+        std::vector<std::thread> pool;
+        for (int t = 0; t < nthreads; ++t)
+            pool.emplace_back([&, t]() {
+                Ctx &c = ctx;
+                c.tid = uint3_emu{(unsigned)t % block.x, ((unsigned)t / block.x) % block.y, (unsigned)t / (block.x * block.y)};
+                c.bdim = block;
+                c.gdim = grid;
+                c.lane = t % 32;
+                for (unsigned b = 0; b < nblocks; ++b) {
+                    c.bid = uint3_emu{b % grid.x, (b / grid.x) % grid.y, b / (grid.x * grid.y)};
+                    c.block = bs.get();
+                    c.warp = bs->warps[t / 32].get();
+                    body();
+                    next_block.arrive_and_wait();
                 }
+                c.block = nullptr;
+                c.warp = nullptr;
+            });
+        for (auto &t : pool) t.join();
         return;
     }
     // CONCURRENT_GRID: every CTA of the launch is alive at once
