@@ -165,4 +165,4 @@ def test_render_rgba_golden_pixels(emu_lib):
 
 
 def test_current_simulation_loop(oracle, emu_lib):
-    P.check_current_simulation(oracle, emu_lib, k=2)      # 3 frames (buffer re-use) run in tests/cpp and on the GPU
+    P.check_current_simulation(oracle, emu_lib)
