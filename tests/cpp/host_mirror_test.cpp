@@ -1,6 +1,6 @@
 // TEST INFRASTRUCTURE.  Drives the C++ host mirror (include/equilibrium.hpp) the way the reference's own callers and
 // tests drive `Fluid`, and compares with the CPU oracle (oracle/fluid_ref.h) bit for bit.  Linked against either the real
-// CUDA library (pytest -m gpu) or the emulated build of the same sources (CPU tests); tests/test_cpp_host.py builds it.
+// CUDA library (pytest -m gpu) or the emulated build of the same sources (CPU tests); tests/test_zz_host_mirrors.py builds it.
 #include <chrono>
 #include <cstdio>
 #include <cstring>

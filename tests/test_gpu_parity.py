@@ -194,6 +194,3 @@ def test_render_rgba_and_snapshots(oracle, cuda_lib, n):
 def test_render_rgba_golden_pixels(cuda_lib):
     P.check_golden_render(cuda_lib)
 
-
-def test_current_simulation_loop(oracle, cuda_lib):
-    P.check_current_simulation(oracle, cuda_lib, n=128, k=6, rect=(80, 80, 110, 110))

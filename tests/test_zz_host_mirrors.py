@@ -1,10 +1,14 @@
-"""The C++ host mirror (include/equilibrium.hpp: the reference's `simulation` API above the C ABI) driven by
+"""Host mirrors of the caller's side.  (Named to sort last: these drive whole frame loops, the kernel parity tests
+run first.)
+
+The C++ host mirror (include/equilibrium.hpp: the reference's `simulation` API above the C ABI) driven by
 tests/cpp/host_mirror_test.cpp and bit-compared with the oracle: on the emulated build here, on the GPU under -m gpu."""
 import os
 import subprocess
 
 import pytest
 
+import parity as P
 from conftest import ROOT
 
 
@@ -29,3 +33,9 @@ def test_cpp_host_mirror_on_the_emulated_build(tmp_path, oracle, emu_lib):
 @pytest.mark.gpu
 def test_cpp_host_mirror_on_the_gpu(tmp_path, oracle, cuda_lib):
     build_and_run(tmp_path, cuda_lib, oracle)
+
+
+@pytest.mark.gpu
+def test_current_simulation_loop_on_the_gpu(oracle, cuda_lib):
+    # the Python mirror of CurrentSimulation on the default scene's grid (the emulated run is in test_emu_parity.py)
+    P.check_current_simulation(oracle, cuda_lib, n=128, k=6, rect=(80, 80, 110, 110))
