@@ -173,6 +173,11 @@ class Fluid:
         nz = self.device_noise(seed, first_frame)
         _lib.check(self._lib, self._lib.eq_step_n_noise(self._h, int(n), C.byref(nz)))
 
+    def add_noise_device(self, seed: int, frame: int):
+        """One device-side add_noise (eq_add_noise): the impulse of Philox counter `frame`, no step."""
+        nz = self.device_noise(seed, frame)
+        _lib.check(self._lib, self._lib.eq_add_noise(self._h, C.byref(nz)))
+
     def add_noise(self):
         x, y, ax, ay = self.noise_impulse()
         self.add_velocity(x, y, ax, ay)

@@ -55,6 +55,19 @@ def test_device_noise_emulated(oracle, emu_lib, n, k, frames, seed, first):
     P.check_device_noise(oracle, emu_lib, n, k, frames, [(10, 12, 30, 20)], seed, first)
 
 
+def test_add_noise_device_equals_the_fused_loop(emu_lib):
+    # { add_noise; step } x 2 through eq_add_noise == eq_step_n_noise(2)
+    n, k = 64, 2
+    a = Fluid(FluidConfigs(), SimulationConfigs(0.02, k, n), lib_path=emu_lib)
+    b = Fluid(FluidConfigs(), SimulationConfigs(0.02, k, n), lib_path=emu_lib)
+    a.step_n_noise(2, 42, first_frame=7)
+    for fr in (7, 8):
+        b.add_noise_device(42, fr)
+        b.step()
+    for name, _ in P.F32_FIELDS:
+        assert P.bits_equal(a.download(name), b.download(name)), name
+
+
 @pytest.mark.parametrize("n", [64, 97, 130])
 def test_add_source_emulated(oracle, emu_lib, n):
     P.check_add_source(oracle, emu_lib, n)
