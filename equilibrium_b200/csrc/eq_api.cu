@@ -30,6 +30,17 @@ static int env_int(const char *name, int dflt) {
     return e ? atoi(e) : dflt;
 }
 
+// Knobs that change RESULTS (dependency waits off, stage-isolation builds) exist only in builds made with
+// -DEQ_DEBUG_KNOBS (scripts/); the default library ignores them.
+static int debug_knob(const char *name) {
+#ifdef EQ_DEBUG_KNOBS
+    return getenv(name) ? 1 : 0;
+#else
+    (void)name;
+    return 0;
+#endif
+}
+
 static thread_local char g_err[512] = "";
 
 static int eq_fail(int code, const char *fmt, ...) {
@@ -440,7 +451,7 @@ static int lin_solve_exact(eq_fluid *h, const LinSolveReq *req, int nreq, int64_
         p.ticket = h->flags;
         p.error = reinterpret_cast<int *>(h->flags + 1);
         p.stats = h->lsx_stats;
-        p.debug_nodeps = getenv("EQ_LSX_NODEPS") ? 1 : 0;
+        p.debug_nodeps = debug_knob("EQ_LSX_NODEPS");
         p.rotate_roles = env_int("EQ_LSX_ROT", 1);
         p.pub_batch = std::max(1, env_int("EQ_LSX_PUBBATCH", L.N >= 8192 ? 8 : 4));
         p.slack = getenv("EQ_LSX_SLACK") ? atoi(getenv("EQ_LSX_SLACK")) : 0;
@@ -551,7 +562,7 @@ static int lin_solve_exact_tb(eq_fluid *h, const LinSolveReq *req, int nreq, int
         p.error = reinterpret_cast<int *>(h->flags + 1);
         p.rotate_roles = env_int("EQ_LSX_ROT", 1);
         p.pub_batch = std::max(1, env_int("EQ_LSX_PUBBATCH", L.N >= 8192 ? 4 : 2));
-        p.debug_nodeps = getenv("EQ_LSX_NODEPS") ? 1 : 0;
+        p.debug_nodeps = debug_knob("EQ_LSX_NODEPS");
         p.passive_fast_frames = (h->all_cols_fluid && env_int("EQ_TB_FAST_FRAMES", 1)) ? 1 : 0;
         p.trace = h->lsx_trace;
         p.trace_g = G - 1;
@@ -933,13 +944,33 @@ extern "C" {
 const char *eq_last_error(void) { return g_err; }
 int eq_abi_version(void) { return EQ_ABI_VERSION; }
 
+// A freshly leased box can answer the very first CUDA call of its life with a transient error
+// (cudaErrorSystemNotReady while the fabric manager is still bringing NVSwitch up,
+// cudaErrorDevicesUnavailable, ...).  Retry for EQ_DEVICE_WAIT_S seconds (default 30) before
+// giving up, and keep the reason in eq_last_error() either way so that callers can print it.
 int eq_device_count(void) {
+    int wait_s = env_int("EQ_DEVICE_WAIT_S", 30);
     int n = 0;
-    if (cudaGetDeviceCount(&n) != cudaSuccess) {
-        cudaGetLastError();
-        return 0;
+    cudaError_t e = cudaSuccess;
+    for (int tries = 0;; tries++) {
+        n = 0;
+        e = cudaGetDeviceCount(&n);
+        if (e == cudaSuccess && n > 0) {
+            g_err[0] = 0;
+            return n;
+        }
+        if (e != cudaSuccess) cudaGetLastError();
+        // "no device" is final on a box without a GPU: do not make CPU-only callers wait
+        if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) break;
+        if (tries * 250 >= wait_s * 1000) break;
+        usleep(250 * 1000);
     }
-    return n;
+    if (e != cudaSuccess)
+        eq_fail(EQ_ERR_CUDA, "cudaGetDeviceCount failed: %s (%s)", cudaGetErrorString(e), cudaGetErrorName(e));
+    else
+        eq_fail(EQ_ERR_CUDA, "cudaGetDeviceCount succeeded but reports 0 devices (CUDA_VISIBLE_DEVICES=%s)",
+                getenv("CUDA_VISIBLE_DEVICES") ? getenv("CUDA_VISIBLE_DEVICES") : "<unset>");
+    return 0;
 }
 
 int eq_destroy(eq_fluid *h) {

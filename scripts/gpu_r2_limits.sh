@@ -7,7 +7,7 @@
 # Run under gpurun on one GPU:  scripts/gpu_r2_limits.sh
 set -e
 mkdir -p gpurun_out variants
-FLAGS="-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false -Xcompiler -fPIC -shared"
+FLAGS="-DEQ_DEBUG_KNOBS -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false -Xcompiler -fPIC -shared"
 for D in NOLOAD NOSTORE NOCOMPUTE; do
   [ -f variants/libeq_dbg_$D.so ] || nvcc $FLAGS -DTBX_DBG_$D -o variants/libeq_dbg_$D.so equilibrium_b200/csrc/eq_api.cu
   [ -f variants/libeq_dbg_SPLIT_$D.so ] || nvcc $FLAGS -DTBX_SPLIT=1 -DTBX_DBG_$D -o variants/libeq_dbg_SPLIT_$D.so equilibrium_b200/csrc/eq_api.cu

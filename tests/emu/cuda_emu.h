@@ -245,7 +245,7 @@ using std::min;
 
 // ---- the sliver of the CUDA runtime that eq_api.cu uses ----------------------
 typedef int cudaError_t;
-enum { cudaSuccess = 0 };
+enum { cudaSuccess = 0, cudaErrorInsufficientDriver = 35, cudaErrorNoDevice = 100 };
 typedef struct eq_emu_stream *cudaStream_t;
 typedef struct eq_emu_event { double t; } *cudaEvent_t;
 enum { cudaStreamNonBlocking = 1, cudaHostAllocDefault = 0 };
@@ -253,6 +253,7 @@ enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpy
 enum { cudaDevAttrMultiProcessorCount = 16, cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 
 static inline const char *cudaGetErrorString(cudaError_t) { return "emulated"; }
+static inline const char *cudaGetErrorName(cudaError_t) { return "emulated"; }
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 static inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }

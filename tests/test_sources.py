@@ -8,7 +8,16 @@ import pytest
 
 import parity as P
 from equilibrium_b200 import EquilibriumError, Fluid, FluidConfigs, SimulationConfigs
-from oracle import pyref
+
+
+class _LazyPyref:
+    """oracle.pyref pulls numba in; keep that out of collection (a `-m gpu` run never needs it at import time)."""
+    def __getattr__(self, name):
+        from oracle import pyref as m
+        return getattr(m, name)
+
+
+pyref = _LazyPyref()
 
 # Random123 kat_vectors, philox4x32 with 10 rounds: counter, key, expected
 PHILOX_KAT = [
