@@ -16,6 +16,7 @@
 #include "eq_common.cuh"
 #include "k_linsolve_exact.cuh"
 #include "k_linsolve_tb.cuh"
+#include "k_linsolve_wf.cuh"
 #include "k_linsolve_rb.cuh"
 #include "k_stencils.cuh"
 #include "k_multigpu.cuh"
@@ -96,6 +97,11 @@ struct eq_fluid {
     uint8_t *codes, *row_fluid, *col_fluid, *chunk_flags, *chunk_flags_tb;
     float *tb_raw[2], *tb_edge[2];   // side streams of the temporally blocked solver
     int tb_ctas;
+    uint8_t *wf_flags;               // register wavefront solver (k_linsolve_wf.cuh): (orientation, band, chunk) summaries,
+    float *wf_raw[2], *wf_edge[2];   // its side streams
+    int wf_ctas;
+    unsigned *wf_dbg;                // EQ_WF_DEBUG=1
+    int wf_dbg_ctas;
     unsigned *counts;       // [4] device
     bool all_cols_fluid;
     uint2 *row_list, *col_list;
@@ -324,6 +330,12 @@ static int ensure_tables(eq_fluid *h) {
     EQ_LAUNCH(k_build_codes, row_grid(h, L.N), 256, 0, h->stream, h->cells, h->codes, h->row_fluid, h->col_fluid,
               h->chunk_flags, h->chunk_flags_tb, h->counts, h->row_list, h->col_list, 1, L);
     TRY(check_launch("k_build_codes(lists)"));
+    {
+        const int NBPw = (L.N + WF_SK + 31) / 32, NCw = L.P / WF_CW;
+        CU(cudaMemsetAsync(h->wf_flags, 0, 3 * (size_t)NBPw * NCw, h->stream));
+        EQ_LAUNCH(k_build_wf_flags, row_grid(h, L.N), 256, 0, h->stream, h->codes, h->wf_flags, NBPw, NCw, L);
+        TRY(check_launch("k_build_wf_flags"));
+    }
     h->n_row = counts[0];
     h->n_col = counts[1];
     h->mask_dirty = false;
@@ -597,6 +609,101 @@ static int lin_solve_exact_tb(eq_fluid *h, const LinSolveReq *req, int nreq, int
     return EQ_OK;
 }
 
+#ifndef EQ_DEFAULT_EXACT_WF
+#define EQ_DEFAULT_EXACT_WF 0   // until k_linsolve_wf beats k_linsolve_tb on the BASELINE configs
+#endif
+// Register-blocked wavefront (k_linsolve_wf.cuh): WF_T iterations per job, passed between the iterations of a job in
+// registers.  Single GPU.
+static int get_wf_job_table(eq_fluid *h, int G, const uint32_t **out) {
+    const int key = -(1 << 20) - G;   // shares the cache with the other tables
+    auto it = h->job_tables->find(key);
+    if (it != h->job_tables->end()) {
+        *out = it->second;
+        return EQ_OK;
+    }
+    const int NBP = (h->L.N + WF_SK + 31) / 32;
+    std::vector<uint32_t> tab;
+    tab.reserve((size_t)G * NBP);
+    for (int w = 0; w <= (NBP - 1) + 2 * (G - 1); ++w)      // w = b + 2g: both dependencies have w-1
+        for (int g = 0; g < G; ++g) {
+            const int b = w - 2 * g;
+            if (b >= 0 && b < NBP) tab.push_back(((uint32_t)g << 16) | (uint32_t)b);
+        }
+    uint32_t *d = nullptr;
+    CU(cudaMalloc(&d, tab.size() * sizeof(uint32_t)));
+    CU(cudaMemcpyAsync(d, tab.data(), tab.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    (*h->job_tables)[key] = d;
+    *out = d;
+    return EQ_OK;
+}
+
+static int lin_solve_exact_wf(eq_fluid *h, const LinSolveReq *req, int nreq, int64_t iters) {
+    if (nreq > 1) {   // one launch per field: a shared launch halves the resident jobs of each chain (see lin_solve_exact_tb)
+        for (int i = 0; i < nreq; ++i) TRY(lin_solve_exact_wf(h, req + i, 1, iters));
+        return EQ_OK;
+    }
+    const EqLayout L = h->L;
+    const int NBP = (L.N + WF_SK + 31) / 32;
+    const int NC = L.P / WF_CW;
+    const int kmax = LSX_KMAX / WF_T * WF_T;
+    int64_t done = 0;
+    while (done < iters) {
+        const int kc = (int)std::min<int64_t>(kmax, iters - done);
+        const int G = (kc + WF_T - 1) / WF_T;
+        const uint32_t *jobs = nullptr;
+        TRY(get_wf_job_table(h, G, &jobs));
+        WfParams p;
+        memset(&p, 0, sizeof(p));
+        p.nprob = nreq;
+        const size_t prog_words = (size_t)G * NBP;
+        if (8 + (size_t)nreq * prog_words > h->flags_words) return eq_fail(EQ_ERR_INVALID, "progress table too small");
+        for (int i = 0; i < nreq; ++i) {
+            p.prob[i].x = req[i].x;
+            p.prob[i].x0 = req[i].x0;
+            p.prob[i].raw = h->wf_raw[i];
+            p.prob[i].edge = h->wf_edge[i];
+            p.prob[i].progress = h->flags + 8 + (size_t)i * prog_words;
+            p.prob[i].a = req[i].a;
+            p.prob[i].c_recip = 1.0f / req[i].c;                       // fluid.rs:311
+            p.prob[i].orient = req[i].orient;
+        }
+        p.codes = h->codes;
+        p.flags = h->wf_flags;
+        p.jobs = jobs;
+        p.njobs = G * NBP;
+        p.N = L.N;
+        p.P = L.P;
+        p.K = kc;
+        p.G = G;
+        p.NBP = NBP;
+        p.NC = NC;
+        p.ticket = h->flags;
+        p.error = reinterpret_cast<int *>(h->flags + 1);
+        p.rotate_roles = env_int("EQ_LSX_ROT", 1);
+        p.pub_batch = std::max(1, env_int("EQ_WF_PUBBATCH", L.N >= 8192 ? 4 : 2));
+        p.force_general = env_int("EQ_WF_GENERAL", 0);
+        p.debug_nodeps = debug_knob("EQ_LSX_NODEPS");
+        CU(cudaMemsetAsync(h->flags, 0, sizeof(unsigned), h->stream));
+        CU(cudaMemsetAsync(h->flags + 8, 0, (size_t)nreq * prog_words * sizeof(unsigned), h->stream));
+        const int grid = std::min(h->wf_ctas, p.njobs * nreq);
+        if (getenv("EQ_WF_DEBUG")) {
+            if (!h->wf_dbg) CU(cudaMalloc(&h->wf_dbg, (size_t)h->wf_ctas * 32 * sizeof(unsigned)));
+            CU(cudaMemsetAsync(h->wf_dbg, 0, (size_t)h->wf_ctas * 32 * sizeof(unsigned), h->stream));
+            h->wf_dbg_ctas = grid;
+            p.dbg = h->wf_dbg;
+        }
+        EQ_LAUNCH(k_linsolve_wf, grid, WF_THREADS, WF_SMEM_BYTES, h->stream, p);
+        TRY(check_launch("k_linsolve_wf"));
+        done += kc;
+    }
+    for (int i = 0; i < nreq; ++i) {
+        EQ_LAUNCH(k_corners, 1, 32, 0, h->stream, req[i].x, L);
+        TRY(check_launch("k_corners"));
+    }
+    return EQ_OK;
+}
+
 // rank r's copy of one of my float arrays (a field or the red-black ping-pong buffer); nullptr outside [0, world)
 static int peer_buffer(eq_fluid *h, const float *mine, int r, float **out) {
     *out = nullptr;
@@ -692,6 +799,10 @@ static int lin_solve(eq_fluid *h, const LinSolveReq *req, int nreq, int64_t iter
     const bool use_tb = (h->world == 1 && TBX_T > 1 && !tb_off);
     const int wave_launches = (int)((iters + LSX_KMAX - 1) / LSX_KMAX) * ((use_tb && !env_int("EQ_TB_BATCH", 0)) ? nreq : 1);
     ProfScope ps(h, CAT_LS, wave_launches + nreq);     // + one corner kernel per field
+    // EQ_EXACT_KERNEL=tb|wf picks the single-GPU kernel (A/B runs)
+    const char *ek = getenv("EQ_EXACT_KERNEL");
+    const bool want_wf = ek ? !strcmp(ek, "wf") : (EQ_DEFAULT_EXACT_WF != 0);
+    if (h->world == 1 && want_wf && !tb_off) return lin_solve_exact_wf(h, req, nreq, iters);
     if (use_tb) return lin_solve_exact_tb(h, req, nreq, iters);
     return lin_solve_exact(h, req, nreq, iters);
 }
@@ -859,6 +970,17 @@ static int alloc_handle(const EqParams *params, eq_fluid **out) {
             CU(cudaMemsetAsync(h->tb_edge[i], 0, nedge * sizeof(float), h->stream));
         }
     }
+    {
+        const int NBPw = (h->L.N + WF_SK + 31) / 32, NCw = h->L.P / WF_CW;
+        CU(cudaMalloc(&h->wf_flags, 3 * (size_t)NBPw * NCw));
+        for (int i = 0; i < 2; ++i) {
+            const size_t nraw = (size_t)WF_T * NBPw * h->L.P, nedge = (size_t)(WF_T - 1) * NBPw * 2 * h->L.P;
+            CU(cudaMalloc(&h->wf_raw[i], nraw * sizeof(float)));
+            CU(cudaMemsetAsync(h->wf_raw[i], 0, nraw * sizeof(float), h->stream));
+            CU(cudaMalloc(&h->wf_edge[i], nedge * sizeof(float)));
+            CU(cudaMemsetAsync(h->wf_edge[i], 0, nedge * sizeof(float), h->stream));
+        }
+    }
     const int NB = (h->L.N - 2 + 31) / 32;
     for (int i = 0; i < 2; ++i) {
         CU(cudaMalloc(&h->raw[i], (size_t)NB * h->L.P * sizeof(float)));
@@ -886,6 +1008,13 @@ static int alloc_handle(const EqParams *params, eq_fluid **out) {
         int tb_per_sm = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tb_per_sm, k_linsolve_tb, TBX_THREADS, TBX_SMEM_BYTES));
         h->tb_ctas = std::max(1, tb_per_sm) * h->sm_count;
+    }
+    {
+        CU(cudaFuncSetAttribute(k_linsolve_wf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WF_SMEM_BYTES));
+        int wf_per_sm = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wf_per_sm, k_linsolve_wf, WF_THREADS, WF_SMEM_BYTES));
+        h->wf_ctas = std::max(1, wf_per_sm) * h->sm_count;
+        if (const char *e = getenv("EQ_WF_CTAS_PER_SM")) h->wf_ctas = std::min(h->wf_ctas, std::max(1, atoi(e)) * h->sm_count);
     }
     if (const char *e = getenv("EQ_LSX_CTAS_PER_SM")) h->lsx_ctas = std::max(1, std::min(per_sm, atoi(e))) * h->sm_count;
     if (const char *e = getenv("EQ_LSX_CTAS_PER_SM")) h->tb_ctas = std::min(h->tb_ctas, std::max(1, atoi(e)) * h->sm_count);
@@ -986,9 +1115,13 @@ int eq_destroy(eq_fluid *h) {
     cudaFree(h->counts);
     cudaFree(h->chunk_flags);
     cudaFree(h->chunk_flags_tb);
+    cudaFree(h->wf_flags);
+    cudaFree(h->wf_dbg);
     for (int i = 0; i < 2; ++i) {
         cudaFree(h->tb_raw[i]);
         cudaFree(h->tb_edge[i]);
+        cudaFree(h->wf_raw[i]);
+        cudaFree(h->wf_edge[i]);
     }
     cudaFree(h->lsx_stats);
     cudaFree(h->lsx_trace);
@@ -1240,6 +1373,17 @@ static int check_device_error(eq_fluid *h) {
     int err = 0;
     CU(cudaMemcpyAsync(&err, h->flags + 1, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
+    if (err != 0 && h->wf_dbg) {
+        std::vector<unsigned> d((size_t)h->wf_dbg_ctas * 32);
+        cudaMemcpy(d.data(), h->wf_dbg, d.size() * sizeof(unsigned), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[wf debug] cta: role(job g.b, index, state) for compute / loader / storer / publisher; state 9 = done\n");
+        for (int c = 0; c < h->wf_dbg_ctas; ++c) {
+            const unsigned *w = d.data() + (size_t)c * 32;
+            fprintf(stderr, "cta %4d:", c);
+            for (int r = 0; r < 4; ++r) fprintf(stderr, "  %u.%u i=%u s=%u |", w[8 * r] >> 16, w[8 * r] & 0xffffu, w[8 * r + 1], w[8 * r + 2]);
+            fprintf(stderr, "\n");
+        }
+    }
     if (err != 0) return eq_fail(EQ_ERR_TIMEOUT, "wavefront watchdog fired (code %d): a lin_solve job waited too long", err);
     return EQ_OK;
 }

@@ -37,6 +37,16 @@
 #define EQ_CODE_COL_UP (1u << 2)
 #define EQ_CODE_COL_DOWN (2u << 2)
 #define EQ_CODE_WALL 0x80u
+// bits 4-6, frame cells only: the Passive frame copies of fluid.rs:182-186 (quirk Q6) written as a mirror code of the
+// FRAME cell, in the unified numbering the register wavefront solver uses for every orientation:
+//   (0, j) takes x[1, j] = R, (N-1, j) takes x[N-2, j] = L   -- if row j holds a NoWall cell
+//   (i, 0) takes x[i, 1] = D, (i, N-1) takes x[i, N-2] = U   -- if column i holds a NoWall cell
+#define EQ_CODE_PASSIVE_SHIFT 4
+#define WF_C_NONE 0u
+#define WF_C_L 1u   // takes x[i-1, j]
+#define WF_C_R 2u   // takes x[i+1, j]
+#define WF_C_U 3u   // takes x[i, j-1]
+#define WF_C_D 4u   // takes x[i, j+1]
 
 struct EqLayout {
     int N;      // grid is N x N
@@ -151,6 +161,12 @@ __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefe
 // mbarrier (shared::cta) -- each barrier gets a 16-byte slot (8 used on the device)
 __device__ __forceinline__ void mbar_init(uint32_t a, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+}
+// re-initialising a live mbarrier is undefined (PTX ISA, mbarrier.init): invalidate it first.  On B200 an init
+// without the inval left the OLD phase in place -- a kernel whose barriers complete an odd number of phases per job
+// then waits on the wrong parity in the next job of the same CTA.
+__device__ __forceinline__ void mbar_inval(uint32_t a) {
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(a) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t a) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");

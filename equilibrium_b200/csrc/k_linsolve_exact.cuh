@@ -68,7 +68,9 @@
 #define LSX_SMEM_BYTES (LSX_MISC_OFF + 16u)
 #define LSX_THREADS 128
 #define LSX_PF 24                                      // L2 prefetch distance of the loader, in chunks
-#define LSX_SPIN_LIMIT (1u << 22)
+#define LSX_SPIN_LIMIT (1u << 22)          // emulated build: spins before a wait gives up
+#define LSX_TIMEOUT_NS 4000000000ull       // device: a wait gives up after 4 s of %globaltimer (a spin count is not a
+                                           // time: jobs deep in the chain legitimately wait tens of ms before their first chunk)
 
 struct LsxProblem {
     float *x;            // in/out, in place
@@ -116,6 +118,18 @@ static inline unsigned long long lsx_gtime() { return 0; }
 #else
 __device__ __forceinline__ unsigned long long lsx_gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #endif
+// watchdog of the waiting loops: `t0` is the time of the first check (0 = not taken yet)
+__device__ __forceinline__ bool lsx_expired(unsigned long long &t0, unsigned spins) {
+#ifdef EQ_HOST_EMU
+    (void)t0;
+    return spins >= LSX_SPIN_LIMIT;
+#else
+    (void)spins;
+    const unsigned long long now = lsx_gtime();
+    if (t0 == 0) t0 = now;
+    return now - t0 > LSX_TIMEOUT_NS;
+#endif
+}
 #define LSX_TRACE(ev, q) do { if (p.trace && lane == 0 && k == p.K - 1 && (b < 3 || b == p.NB - 1) && (q) >= 200 && (q) < 328) p.trace[((size_t)(b < 3 ? b : 3) * 8 + (ev)) * 128 + (q) - 200] = lsx_gtime(); } while (0)
 #define LSX_STAT(slot, v) do { if (p.stats && lane == 0) atomicAdd(p.stats + (slot), (unsigned long long)(v)); } while (0)
 
@@ -129,6 +143,7 @@ __device__ __forceinline__ bool lsx_wait_flags(const unsigned *f1, unsigned n1, 
                                                bool sys2, int *error, int lane) {
     bool ok = true;
     unsigned spins = 0;
+    unsigned long long t0 = 0;
     // spin with relaxed loads (an acquire load is followed by an L1 invalidate, CCTL.IVALL, which
     // the five loaders of an SM would otherwise issue every few hundred cycles), then take one
     // acquire load of the flag that was seen set: it reads from the release and synchronises.
@@ -137,7 +152,7 @@ __device__ __forceinline__ bool lsx_wait_flags(const unsigned *f1, unsigned n1, 
            (f2 && (sys2 ? ld_relaxed_sys_u32(f2) : ld_relaxed_u32(f2)) < n2)) {
         __nanosleep(64);
         if ((++spins & 1023u) == 0) {
-            if (spins >= LSX_SPIN_LIMIT) {
+            if (lsx_expired(t0, spins)) {
                 if (lane == 0) *error = 1;
                 ok = false;
                 break;
@@ -158,9 +173,10 @@ __device__ __forceinline__ bool lsx_wait_flags(const unsigned *f1, unsigned n1, 
 __device__ __forceinline__ bool lsx_wait_bar(uint32_t bar, uint32_t parity, int *error, int lane) {
     bool ok = true;
     unsigned spins = 0;
+    unsigned long long t0 = 0;
     while (!mbar_try_wait(bar, parity)) {
         if ((++spins & 255u) == 0) {
-            if (spins >= LSX_SPIN_LIMIT) {
+            if (lsx_expired(t0, spins)) {
                 if (lane == 0) *error = 2;
                 ok = false;
                 break;
@@ -368,11 +384,12 @@ struct LsxJob {
         while (q < NC && ok) {
             if (lane == 0) {
                 unsigned spins = 0;
+                unsigned long long t0 = 0;
                 int have;
                 while ((have = (int)lds_acquire_cta_u32(cnt)) < min(q + p.pub_batch, NC)) {     // chunks whose stores are issued
                     __nanosleep(64);
                     if ((++spins & 1023u) == 0) {
-                        if (spins >= LSX_SPIN_LIMIT) { *p.error = 3; ok = 0; break; }
+                        if (lsx_expired(t0, spins)) { *p.error = 3; ok = 0; break; }
                         if (ld_volatile_s32(p.error) != 0) { ok = 0; break; }
                     }
                 }
@@ -526,7 +543,10 @@ __global__ void __launch_bounds__(LSX_THREADS) k_linsolve_exact(const LsxParams 
     // broadcast the warp index so the compiler knows the role branches below are warp-uniform
     // (otherwise every __shfl/__syncwarp in the roles becomes an out-of-line WARPSYNC.COLLECTIVE)
     const int lane = (int)threadIdx.x & 31;
-    if (threadIdx.x == 0) sts_u32(sbase + LSX_MISC_OFF + 8u, p.rotate_roles ? eq_cta_slot_rotation() : 0u);
+    if (threadIdx.x == 0) {
+        sts_u32(sbase + LSX_MISC_OFF + 8u, p.rotate_roles ? eq_cta_slot_rotation() : 0u);
+        for (int i = 0; i < 3 * LSX_SLOTS; ++i) mbar_init(sbase + LSX_BAR_OFF + (uint32_t)i * 16u, 1u);
+    }
     __syncthreads();
     // role 0 compute, 1 loader, 2 storer, 3 publisher (uniform per warp: taken through a shuffle so that
     // the compiler keeps the dispatch branch-uniform)
@@ -537,6 +557,7 @@ __global__ void __launch_bounds__(LSX_THREADS) k_linsolve_exact(const LsxParams 
             const unsigned t = (ld_volatile_s32(p.error) != 0) ? 0xffffffffu : atomicAdd(p.ticket, 1u);
             sts_u32(sbase + LSX_MISC_OFF, t);
             sts_u32(sbase + LSX_MISC_OFF + 4u, 0u);
+            for (int i = 0; i < 3 * LSX_SLOTS; ++i) mbar_inval(sbase + LSX_BAR_OFF + (uint32_t)i * 16u);   // see mbar_inval
             for (int i = 0; i < LSX_SLOTS; ++i) {
                 mbar_init(sbase + LSX_BAR_OFF + (uint32_t)i * 16u, 32u);                       // full: 32 loader lanes
                 mbar_init(sbase + LSX_BAR_OFF + (uint32_t)(LSX_SLOTS + i) * 16u, 1u);          // done: compute lane 0

@@ -297,11 +297,12 @@ struct TbxJob {
         while (q < NC && ok) {
             if (lane == 0) {
                 unsigned spins = 0;
+                unsigned long long t0 = 0;
                 int have;
                 while ((have = (int)lds_acquire_cta_u32(cnt)) < min(q + p.pub_batch, NC)) {
                     __nanosleep(64);
                     if ((++spins & 1023u) == 0) {
-                        if (spins >= LSX_SPIN_LIMIT) { *p.error = 3; ok = 0; break; }
+                        if (lsx_expired(t0, spins)) { *p.error = 3; ok = 0; break; }
                         if (ld_volatile_s32(p.error) != 0) { ok = 0; break; }
                     }
                 }
@@ -617,7 +618,11 @@ __global__ void __launch_bounds__(TBX_THREADS, 5) k_linsolve_tb(const TbxParams 
     const uint32_t sbase = smem_u32(tbx_smem_raw);
     const int total = p.njobs * p.nprob;
     const int lane = (int)threadIdx.x & 31;
-    if (threadIdx.x == 0) sts_u32(sbase + TBX_MISC_OFF + 8u, (p.rotate_roles && !TBX_SPLIT) ? eq_cta_slot_rotation() : 0u);
+    if (threadIdx.x == 0) {
+        sts_u32(sbase + TBX_MISC_OFF + 8u, (p.rotate_roles && !TBX_SPLIT) ? eq_cta_slot_rotation() : 0u);
+        for (int i = 0; i < 3 * TBX_SLOTS; ++i) mbar_init(sbase + TBX_BAR_OFF + (uint32_t)i * 16u, 1u);
+        mbar_init(sbase + TBX_AB_OFF, 1u);
+    }
     __syncthreads();
     // role 0 compute, 1 loader, 2 storer, 3 publisher (uniform per warp: taken through a shuffle so that
     // the compiler keeps the dispatch branch-uniform)
@@ -630,6 +635,8 @@ __global__ void __launch_bounds__(TBX_THREADS, 5) k_linsolve_tb(const TbxParams 
             const unsigned t = (ld_volatile_s32(p.error) != 0) ? 0xffffffffu : atomicAdd(p.ticket, 1u);
             sts_u32(sbase + TBX_MISC_OFF, t);
             sts_u32(sbase + TBX_MISC_OFF + 4u, 0u);
+            for (int i = 0; i < 3 * TBX_SLOTS; ++i) mbar_inval(sbase + TBX_BAR_OFF + (uint32_t)i * 16u);   // see mbar_inval
+            mbar_inval(sbase + TBX_AB_OFF);
             for (int i = 0; i < TBX_SLOTS; ++i) {
                 mbar_init(sbase + TBX_BAR_OFF + (uint32_t)i * 16u, 32u);
                 mbar_init(sbase + TBX_BAR_OFF + (uint32_t)(TBX_SLOTS + i) * 16u, 1u);

@@ -71,7 +71,14 @@ __global__ void k_build_codes(const uint8_t *__restrict__ cells, uint8_t *__rest
             if (j / 32 < NB)   // row j is also row j0-1 of the band below (cross-band DOWN patch)
                 chunk_flags[(size_t)NB * NC + (size_t)(j / 32) * NC + i / EQ_LSX_CW] = 1;
         }
-    } else if (j >= L.row0 && j < L.row1) {
+    } else {
+        // Passive frame copies as mirror codes of the frame cells (bits 4-6; needs the flags of pass 0)
+        unsigned pc = WF_C_NONE;
+        if (j >= 1 && j <= L.N - 2 && row_fluid[j]) pc = (i == 0) ? WF_C_R : ((i == L.N - 1) ? WF_C_L : pc);
+        if (i >= 1 && i <= L.N - 2 && col_fluid[i]) pc = (j == 0) ? WF_C_D : ((j == L.N - 1) ? WF_C_U : pc);
+        if (pc) codes[o] = (uint8_t)(code | (pc << EQ_CODE_PASSIVE_SHIFT));
+    }
+    if (pass == 1 && j >= L.row0 && j < L.row1) {
         if (code & 3u) {
             const unsigned slot = atomicAdd(&counts[2], 1u);
             row_list[slot] = make_uint2(o, (code & 3u) == EQ_CODE_ROW_RIGHT ? o + 1u : o - 1u);

@@ -191,6 +191,7 @@ static inline void mbar_init(uint32_t a, uint32_t count) {
     eq_emu_mbar *m = eq_emu_mb(a);
     m->pending.store(count); m->phase.store(0); m->count = count;
 }
+static inline void mbar_inval(uint32_t) {}
 static inline void mbar_arrive(uint32_t a) {
     eq_emu_mbar *m = eq_emu_mb(a);
     if (m->pending.fetch_sub(1, std::memory_order_acq_rel) == 1) {
