@@ -100,6 +100,7 @@ struct eq_fluid {
     uint8_t *wf_flags;               // register wavefront solver (k_linsolve_wf.cuh): (orientation, band, chunk) summaries,
     float *wf_raw[2], *wf_edge[2];   // its side streams
     int wf_ctas;
+    unsigned long long *wf_trace;    // EQ_WF_TRACE=1
     unsigned *wf_dbg;                // EQ_WF_DEBUG=1
     int wf_dbg_ctas;
     unsigned *counts;       // [4] device
@@ -669,6 +670,7 @@ static int lin_solve_exact_wf(eq_fluid *h, const LinSolveReq *req, int nreq, int
             p.prob[i].orient = req[i].orient;
         }
         p.codes = h->codes;
+        p.row_fluid = h->row_fluid;
         p.flags = h->wf_flags;
         p.jobs = jobs;
         p.njobs = G * NBP;
@@ -687,6 +689,17 @@ static int lin_solve_exact_wf(eq_fluid *h, const LinSolveReq *req, int nreq, int
         CU(cudaMemsetAsync(h->flags, 0, sizeof(unsigned), h->stream));
         CU(cudaMemsetAsync(h->flags + 8, 0, (size_t)nreq * prog_words * sizeof(unsigned), h->stream));
         const int grid = std::min(h->wf_ctas, p.njobs * nreq);
+        unsigned long long *jt = nullptr;
+        if (getenv("EQ_WF_JOBTIMES")) {
+            CU(cudaMalloc(&jt, 4 * (size_t)p.njobs * sizeof(unsigned long long)));
+            CU(cudaMemsetAsync(jt, 0, 4 * (size_t)p.njobs * sizeof(unsigned long long), h->stream));
+            p.jobtimes = jt;
+        }
+        if (getenv("EQ_WF_TRACE")) {
+            if (!h->wf_trace) CU(cudaMalloc(&h->wf_trace, 64 * 16 * sizeof(unsigned long long)));
+            CU(cudaMemsetAsync(h->wf_trace, 0, 64 * 16 * sizeof(unsigned long long), h->stream));
+            p.trace = h->wf_trace;
+        }
         if (getenv("EQ_WF_DEBUG")) {
             if (!h->wf_dbg) CU(cudaMalloc(&h->wf_dbg, (size_t)h->wf_ctas * 32 * sizeof(unsigned)));
             CU(cudaMemsetAsync(h->wf_dbg, 0, (size_t)h->wf_ctas * 32 * sizeof(unsigned), h->stream));
@@ -695,6 +708,36 @@ static int lin_solve_exact_wf(eq_fluid *h, const LinSolveReq *req, int nreq, int
         }
         EQ_LAUNCH(k_linsolve_wf, grid, WF_THREADS, WF_SMEM_BYTES, h->stream, p);
         TRY(check_launch("k_linsolve_wf"));
+        if (jt) {
+            std::vector<unsigned long long> t(4 * (size_t)p.njobs);
+            CU(cudaStreamSynchronize(h->stream));
+            CU(cudaMemcpy(t.data(), jt, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+            cudaFree(jt);
+            if (FILE *f = fopen(getenv("EQ_WF_JOBTIMES"), "w")) {
+                fprintf(f, "# G=%d NBP=%d ; g b ticket_ns flags_ns full0_ns done_ns\n", G, NBP);
+                for (int gg = 0; gg < G; ++gg)
+                    for (int bb = 0; bb < NBP; ++bb) {
+                        const unsigned long long *e = t.data() + 4 * ((size_t)gg * NBP + bb);
+                        fprintf(f, "%d %d %llu %llu %llu %llu\n", gg, bb, e[0], e[1], e[2], e[3]);
+                    }
+                fclose(f);
+            }
+        }
+        if (p.trace) {
+            static const char *names[16] = {"loader.start", "flags0.ok", "wave0.issued", "full0.seen", "macro0.done", "macro2.done",
+                                            "macro3.done", "chunk0.stored", "chunk0.published", "flags4.ok", "macro7.done",
+                                            "macro63.done", "macro127.done", "-", "-", "-"};
+            std::vector<unsigned long long> t(64 * 16);
+            CU(cudaStreamSynchronize(h->stream));
+            CU(cudaMemcpy(t.data(), h->wf_trace, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+            const unsigned long long t0 = t[0];
+            fprintf(stderr, "[wf trace, us since band 0's loader started; group 0]\n");
+            for (int bb = 0; bb < std::min(64, NBP); bb += (bb < 8 ? 1 : 8)) {
+                fprintf(stderr, "band %2d:", bb);
+                for (int e = 0; e < 13; ++e) fprintf(stderr, " %s=%.1f", names[e], t[bb * 16 + e] ? (double)(t[bb * 16 + e] - t0) / 1e3 : -1.0);
+                fprintf(stderr, " | compute warp kcycles: wait_full=%.0f pre=%.0f body=%.0f\n", t[bb * 16 + 13] / 1e3, t[bb * 16 + 14] / 1e3, t[bb * 16 + 15] / 1e3);
+            }
+        }
         done += kc;
     }
     for (int i = 0; i < nreq; ++i) {
@@ -1117,6 +1160,7 @@ int eq_destroy(eq_fluid *h) {
     cudaFree(h->chunk_flags_tb);
     cudaFree(h->wf_flags);
     cudaFree(h->wf_dbg);
+    cudaFree(h->wf_trace);
     for (int i = 0; i < 2; ++i) {
         cudaFree(h->tb_raw[i]);
         cudaFree(h->tb_edge[i]);

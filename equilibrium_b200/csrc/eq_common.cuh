@@ -212,6 +212,20 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
 }
 #endif  // !EQ_HOST_EMU
 
+// Predicated stores as ONE instruction (an `if` around a store in the middle of an unrolled, shuffle-heavy loop makes the
+// compiler treat the warp as possibly divergent from there on: every later shuffle becomes WARPSYNC.COLLECTIVE + SHFL).
+#ifdef EQ_HOST_EMU
+static inline void st_shared_f32_if(bool p, uint32_t a, float v) { if (p) sts_f32(a, v); }
+static inline void st_global_f32_if(bool p, float *ptr, float v) { if (p) *ptr = v; }
+#else
+__device__ __forceinline__ void st_shared_f32_if(bool p, uint32_t a, float v) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %0, 0;\n\t@q st.shared.f32 [%1], %2;\n\t}" ::"r"((unsigned)p), "r"(a), "f"(v) : "memory");
+}
+__device__ __forceinline__ void st_global_f32_if(bool p, float *ptr, float v) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %0, 0;\n\t@q st.global.f32 [%1], %2;\n\t}" ::"r"((unsigned)p), "l"(ptr), "f"(v) : "memory");
+}
+#endif
+
 // The Gauss-Seidel update of fluid.rs:315-320 with the reference's expression
 // tree: (x0 + a * (((right + left) + down) + up)) * c_recip, every operation
 // individually rounded (no FMA: rustc never contracts).

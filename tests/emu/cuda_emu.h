@@ -232,6 +232,8 @@ static inline double atomicAdd(double *p, double v) {
 }
 
 // ---- arithmetic intrinsics (compile with -ffp-contract=off) ------------------
+static inline unsigned __float_as_uint(float v) { unsigned u; memcpy(&u, &v, 4); return u; }
+static inline float __uint_as_float(unsigned u) { float v; memcpy(&v, &u, 4); return v; }
 static inline float __fadd_rn(float a, float b) { return a + b; }
 static inline float __fsub_rn(float a, float b) { return a - b; }
 static inline float __fmul_rn(float a, float b) { return a * b; }
