@@ -100,6 +100,8 @@ struct eq_fluid {
     uint8_t *wf_flags;               // register wavefront solver (k_linsolve_wf.cuh): (orientation, band, chunk) summaries,
     float *wf_raw[2], *wf_edge[2];   // its side streams
     int wf_ctas;
+    unsigned *a0_flags;              // [2] guard results of the a == 0 shortcut (k_a0_check), one per request
+    const unsigned *run_if;          // set around the solver launches of a request whose shortcut is armed
     unsigned long long *wf_trace;    // EQ_WF_TRACE=1
     unsigned *wf_dbg;                // EQ_WF_DEBUG=1
     int wf_dbg_ctas;
@@ -487,7 +489,10 @@ static int lin_solve_exact(eq_fluid *h, const LinSolveReq *req, int nreq, int64_
         // F_{-1} and (b) is a barrier with both neighbours, so nobody publishes into a progress
         // mirror that has not been cleared yet.
         for (int i = 0; i < nreq; ++i) TRY(halo_xchg(h, req[i].x));
-        const int grid = std::min(h->lsx_ctas, p.njobs * nreq);
+        // odd number of phases per mbarrier slot and job (NC not a multiple of 2 * slots): one job per CTA
+        p.single_shot = (NC % (2 * LSX_SLOTS)) != 0 ? 1 : 0;
+        p.run_if = h->run_if;
+        const int grid = p.single_shot ? p.njobs * nreq : std::min(h->lsx_ctas, p.njobs * nreq);
         EQ_LAUNCH(k_linsolve_exact, grid, LSX_THREADS, LSX_SMEM_BYTES, h->stream, p);
         TRY(check_launch("k_linsolve_exact"));
         // ... and afterwards it waits until the neighbour's solver (which patches my last row and
@@ -598,7 +603,9 @@ static int lin_solve_exact_tb(eq_fluid *h, const LinSolveReq *req, int nreq, int
         }
         CU(cudaMemsetAsync(h->flags, 0, sizeof(unsigned), h->stream));
         CU(cudaMemsetAsync(h->flags + 8, 0, (size_t)nreq * prog_words * sizeof(unsigned), h->stream));
-        const int grid = std::min(h->tb_ctas, p.njobs * nreq);
+        p.single_shot = (NC % (2 * TBX_SLOTS)) != 0 ? 1 : 0;   // odd number of phases per mbarrier slot and job: one job per CTA
+        p.run_if = h->run_if;
+        const int grid = p.single_shot ? p.njobs * nreq : std::min(h->tb_ctas, p.njobs * nreq);
         EQ_LAUNCH(k_linsolve_tb, grid, TBX_THREADS, TBX_SMEM_BYTES, h->stream, p);
         TRY(check_launch("k_linsolve_tb"));
         done += kc;
@@ -685,6 +692,7 @@ static int lin_solve_exact_wf(eq_fluid *h, const LinSolveReq *req, int nreq, int
         p.rotate_roles = env_int("EQ_LSX_ROT", 1);
         p.pub_batch = std::max(1, env_int("EQ_WF_PUBBATCH", L.N >= 8192 ? 4 : 2));
         p.force_general = env_int("EQ_WF_GENERAL", 0);
+        p.run_if = h->run_if;
         p.debug_nodeps = debug_knob("EQ_LSX_NODEPS");
         CU(cudaMemsetAsync(h->flags, 0, sizeof(unsigned), h->stream));
         CU(cudaMemsetAsync(h->flags + 8, 0, (size_t)nreq * prog_words * sizeof(unsigned), h->stream));
@@ -808,20 +816,27 @@ static int lin_solve_red_black(eq_fluid *h, const LinSolveReq *req, int nreq, in
                 }
                 EQ_LAUNCH(k_rb_reg, grid_r, RBR_THREADS, RBR_SMEM_BYTES, h->stream, cur, other, req[i].x0, h->codes,
                           h->chunk_flags, h->row_fluid, h->col_fluid, req[i].a, c_recip, req[i].orient, it, L.row0, L.row1,
-                          ty0, pu, pd, L, sy);
+                          ty0, pu, pd, h->run_if, L, sy);
 #else
                 EQ_LAUNCH(k_rb_reg, grid_r, RBR_THREADS, RBR_SMEM_BYTES, h->stream, cur, other, req[i].x0, h->codes,
                           h->chunk_flags, h->row_fluid, h->col_fluid, req[i].a, c_recip, req[i].orient, it, L.row0, L.row1,
-                          ty0, pu, pd, L);
+                          ty0, pu, pd, h->run_if, L);
 #endif
                 TRY(check_launch("k_rb_reg"));
                 pushed = (h->world > 1);
             }
             std::swap(cur, other);
         }
-        if (cur != req[i].x)
-            CU(cudaMemcpyAsync(req[i].x + (size_t)L.row0 * L.P, cur + (size_t)L.row0 * L.P,
-                               (size_t)rows * L.P * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+        if (cur != req[i].x) {
+            if (h->run_if) {      // the launches above may have been skipped (a == 0 shortcut): then `cur` holds nothing
+                const dim3 g((unsigned)((L.P / 4 + 255) / 256), (unsigned)std::min(rows, 1024), 1);
+                EQ_LAUNCH(k_copy_rows_if, g, 256, 0, h->stream, req[i].x, cur, h->run_if, L.row0, L.row1, L);
+                TRY(check_launch("k_copy_rows_if"));
+            } else {
+                CU(cudaMemcpyAsync(req[i].x + (size_t)L.row0 * L.P, cur + (size_t)L.row0 * L.P,
+                                   (size_t)rows * L.P * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+            }
+        }
         EQ_LAUNCH(k_corners, 1, 32, 0, h->stream, req[i].x, L);
         TRY(check_launch("k_corners"));
         TRY(halo_xchg(h, req[i].x));
@@ -829,19 +844,61 @@ static int lin_solve_red_black(eq_fluid *h, const LinSolveReq *req, int nreq, in
     return EQ_OK;
 }
 
+static int set_boundaries(eq_fluid *h, int orient, float *x);
+static int lin_solve_dispatch(eq_fluid *h, const LinSolveReq *req, int nreq, int64_t iters);
+
+// a == 0, c == 1 (k_a0_check in k_stencils.cuh): guard, copy, the solver behind the guard's flag, one set_boundaries.
+static bool a0_shortcut_applies(const eq_fluid *h, const LinSolveReq &r) {
+    static const bool off = getenv("EQ_A0_FASTPATH") && atoi(getenv("EQ_A0_FASTPATH")) == 0;
+    return !off && h->world == 1 && r.a == 0.0f && !std::signbit(r.a) && r.c == 1.0f;
+}
+
+static int lin_solve_a0(eq_fluid *h, const LinSolveReq &r, int slot, int64_t iters) {
+    const EqLayout L = h->L;
+    unsigned *flag = h->a0_flags + slot;
+    {
+        ProfScope ps(h, CAT_OTHER, 2);
+        CU(cudaMemsetAsync(flag, 0, sizeof(unsigned), h->stream));
+        const dim3 grid((unsigned)((L.N + 4 * 256 - 1) / (4 * 256)), (unsigned)std::min(L.N, 2048), 1);
+        EQ_LAUNCH(k_a0_check, grid, 256, 0, h->stream, r.x, r.x0, flag, L);
+        TRY(check_launch("k_a0_check"));
+        EQ_LAUNCH(k_a0_apply, grid, 256, 0, h->stream, r.x, r.x0, flag, L);
+        TRY(check_launch("k_a0_apply"));
+    }
+    h->run_if = flag;
+    const int rc = lin_solve_dispatch(h, &r, 1, iters);     // returns at once on the device unless the guard failed
+    h->run_if = nullptr;
+    TRY(rc);
+    return set_boundaries(h, r.orient, r.x);                 // idempotent after a real solve
+}
+
 static int lin_solve(eq_fluid *h, const LinSolveReq *req, int nreq, int64_t iters) {
     if (iters <= 0) return EQ_OK;   // `for _k in 0..frames` runs zero times
     TRY(ensure_tables(h));
+    bool any_a0 = false;
+    for (int i = 0; i < nreq; ++i) any_a0 = any_a0 || a0_shortcut_applies(h, req[i]);
+    if (any_a0) {
+        for (int i = 0; i < nreq; ++i) {
+            if (a0_shortcut_applies(h, req[i])) TRY(lin_solve_a0(h, req[i], i & 1, iters));
+            else TRY(lin_solve_dispatch(h, req + i, 1, iters));
+        }
+        return EQ_OK;
+    }
+    return lin_solve_dispatch(h, req, nreq, iters);
+}
+
+static int lin_solve_dispatch(eq_fluid *h, const LinSolveReq *req, int nreq, int64_t iters) {
     const int64_t cells = (int64_t)(h->L.N - 2) * owned_interior_rows(h);
-    h->prof_cell_iters += cells * iters * nreq;
+    const int ls_cat = h->run_if ? CAT_OTHER : CAT_LS;      // a solve behind the a == 0 guard normally does no sweeps: not lin_solve time
+    if (!h->run_if) h->prof_cell_iters += cells * iters * nreq;
     if (h->prm.mode == EQ_MODE_RED_BLACK) {
-        ProfScope ps(h, CAT_LS, (int)(((iters + RB_T - 1) / RB_T + 1) * nreq));
+        ProfScope ps(h, ls_cat, (int)(((iters + RB_T - 1) / RB_T + 1) * nreq));
         return lin_solve_red_black(h, req, nreq, iters);
     }
     static const bool tb_off = getenv("EQ_LSX_TB") && atoi(getenv("EQ_LSX_TB")) == 0;
     const bool use_tb = (h->world == 1 && TBX_T > 1 && !tb_off);
     const int wave_launches = (int)((iters + LSX_KMAX - 1) / LSX_KMAX) * ((use_tb && !env_int("EQ_TB_BATCH", 0)) ? nreq : 1);
-    ProfScope ps(h, CAT_LS, wave_launches + nreq);     // + one corner kernel per field
+    ProfScope ps(h, ls_cat, wave_launches + nreq);     // + one corner kernel per field
     // EQ_EXACT_KERNEL=tb|wf picks the single-GPU kernel (A/B runs)
     const char *ek = getenv("EQ_EXACT_KERNEL");
     const bool want_wf = ek ? !strcmp(ek, "wf") : (EQ_DEFAULT_EXACT_WF != 0);
@@ -1001,6 +1058,7 @@ static int alloc_handle(const EqParams *params, eq_fluid **out) {
     CU(cudaMalloc(&h->row_fluid, h->L.N));
     CU(cudaMalloc(&h->col_fluid, h->L.P));
     CU(cudaMalloc(&h->counts, 4 * sizeof(unsigned)));
+    CU(cudaMalloc(&h->a0_flags, 2 * sizeof(unsigned)));
     CU(cudaMalloc(&h->chunk_flags, 2 * (size_t)((h->L.N - 2 + 31) / 32) * ((h->L.N + EQ_LSX_CW - 1) / EQ_LSX_CW)));
     {
         const int NBP = (h->L.N - 2 + TBX_SK + 31) / 32;
@@ -1156,6 +1214,7 @@ int eq_destroy(eq_fluid *h) {
     cudaFree(h->row_fluid);
     cudaFree(h->col_fluid);
     cudaFree(h->counts);
+    cudaFree(h->a0_flags);
     cudaFree(h->chunk_flags);
     cudaFree(h->chunk_flags_tb);
     cudaFree(h->wf_flags);

@@ -103,6 +103,10 @@ struct LsxParams {
                                  // costs ~4 us of fence whatever it covers; one chunk per release paces the whole chain
     int rotate_roles;            // 1: spread the roles over the warp schedulers (eq_cta_slot_rotation); EQ_LSX_ROT=0 turns it off
     int debug_nodeps;            // EQ_LSX_NODEPS=1: skip the dependency waits (WRONG results; throughput experiments only)
+    const unsigned *run_if;      // not null: return at once when *run_if == 0 (the a == 0 shortcut was taken, k_a0_check)
+    int single_shot;             // one job per CTA (grid = jobs): set when a job completes an ODD number of phases per mbarrier
+                                 // slot -- re-initialising the barriers for a second job of the same CTA does not take on B200
+                                 // (profiles/r02_wf_notes.md, section 3), the next job would wait on the wrong parity
     unsigned long long *stats;   // optional [16] cycle counters (EQ_LSX_STATS=1), see eq_api.cu
     unsigned long long *jobtimes; // optional [2 * njobs * nprob] start/end ns of every job (EQ_LSX_JOBTIMES=1)
     unsigned long long *trace;   // optional event trace of the first jobs (EQ_LSX_TRACE=1): [4 bands][8 events][128 chunks] ns
@@ -537,16 +541,14 @@ struct LsxJob {
 
 // Four warps per CTA (compute / loader / storer / publisher); persistent CTAs pull jobs from the ticket counter.
 __global__ void __launch_bounds__(LSX_THREADS) k_linsolve_exact(const LsxParams p) {
+    if (p.run_if && *p.run_if == 0u) return;
     EQ_DYN_SMEM(lsx_smem_raw);
     const uint32_t sbase = smem_u32(lsx_smem_raw);
     const int total = p.njobs * p.nprob;
     // broadcast the warp index so the compiler knows the role branches below are warp-uniform
     // (otherwise every __shfl/__syncwarp in the roles becomes an out-of-line WARPSYNC.COLLECTIVE)
     const int lane = (int)threadIdx.x & 31;
-    if (threadIdx.x == 0) {
-        sts_u32(sbase + LSX_MISC_OFF + 8u, p.rotate_roles ? eq_cta_slot_rotation() : 0u);
-        for (int i = 0; i < 3 * LSX_SLOTS; ++i) mbar_init(sbase + LSX_BAR_OFF + (uint32_t)i * 16u, 1u);
-    }
+    if (threadIdx.x == 0) sts_u32(sbase + LSX_MISC_OFF + 8u, p.rotate_roles ? eq_cta_slot_rotation() : 0u);
     __syncthreads();
     // role 0 compute, 1 loader, 2 storer, 3 publisher (uniform per warp: taken through a shuffle so that
     // the compiler keeps the dispatch branch-uniform)
@@ -557,7 +559,7 @@ __global__ void __launch_bounds__(LSX_THREADS) k_linsolve_exact(const LsxParams 
             const unsigned t = (ld_volatile_s32(p.error) != 0) ? 0xffffffffu : atomicAdd(p.ticket, 1u);
             sts_u32(sbase + LSX_MISC_OFF, t);
             sts_u32(sbase + LSX_MISC_OFF + 4u, 0u);
-            for (int i = 0; i < 3 * LSX_SLOTS; ++i) mbar_inval(sbase + LSX_BAR_OFF + (uint32_t)i * 16u);   // see mbar_inval
+            // (re-initialised per job: only sound while a job completes an even number of phases per slot, see single_shot)
             for (int i = 0; i < LSX_SLOTS; ++i) {
                 mbar_init(sbase + LSX_BAR_OFF + (uint32_t)i * 16u, 32u);                       // full: 32 loader lanes
                 mbar_init(sbase + LSX_BAR_OFF + (uint32_t)(LSX_SLOTS + i) * 16u, 1u);          // done: compute lane 0
@@ -585,6 +587,7 @@ __global__ void __launch_bounds__(LSX_THREADS) k_linsolve_exact(const LsxParams 
         else LSX_DISPATCH(EQ_PASSIVE)
 #undef LSX_DISPATCH
         if (p.jobtimes && threadIdx.x == 0) p.jobtimes[2 * ((size_t)(k * p.NB + b) * p.nprob + pi) + 1] = lsx_gtime();
+        if (p.single_shot) break;
         // a role that gave up has set *p.error (or seen it set); the next pass of the loop makes
         // thread 0 read it and every thread leaves together
     }

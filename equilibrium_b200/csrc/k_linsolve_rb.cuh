@@ -225,7 +225,8 @@ __global__ void __launch_bounds__(RBR_THREADS, 8 / RBR_WARPS) k_rb_reg(const flo
                                                            const uint8_t *__restrict__ col_fluid, float a, float c_recip,
                                                            int orient, int iters, int row_lo, int row_hi, int tile_y0,
                                                            float *__restrict__ peer_up_out, float *__restrict__ peer_down_out,
-                                                           EqLayout L RBR_SYNC_PARAM) {
+                                                           const unsigned *__restrict__ run_if, EqLayout L RBR_SYNC_PARAM) {
+    if (run_if && *run_if == 0u) return;                                  // the a == 0 shortcut was taken (k_a0_check)
     EQ_DYN_SMEM(rbr_smem);
     float *x0s = reinterpret_cast<float *>(rbr_smem);                    // [2][RBR_H][RBR_THREADS], thread-private slots
     float *edge = reinterpret_cast<float *>(rbr_smem + RBR_EDGE_OFF);     // [warp][side][row]
@@ -456,6 +457,9 @@ __global__ void __launch_bounds__(RBR_THREADS, 8 / RBR_WARPS) k_rb_reg(const flo
             else if (orient == EQ_ADJUST_COLUMN) fixup(std::integral_constant<int, EQ_ADJUST_COLUMN>{});
             else fixup(std::integral_constant<int, EQ_PASSIVE>{});
             if (it + 1 < iters) {
+                // the neighbouring warps may still be reading my edge columns inside their fixup (the values they mirror are
+                // never changed by the pass, so the overlap was benign -- compute-sanitizer racecheck rightly flags it)
+                __syncthreads();
 #pragma unroll
                 for (int y = 0; y < RBR_H; ++y) {
                     const float ev = (lane == 0) ? v[y][0] : v[y][1];

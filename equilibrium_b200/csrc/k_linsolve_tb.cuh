@@ -90,6 +90,8 @@ struct TbxParams {
                                  // costs ~4 us of fence whatever it covers; one chunk per release paces the whole chain
     int rotate_roles;            // see LsxParams
     int debug_nodeps;            // EQ_LSX_NODEPS=1: skip the dependency waits (WRONG results; throughput experiments only)
+    const unsigned *run_if;      // not null: return at once when *run_if == 0 (see LsxParams::run_if)
+    int single_shot;             // one job per CTA (see LsxParams::single_shot)
     int passive_fast_frames;     // every interior column has a NoWall cell: Passive frame-row copies are unconditional
     int trace_g, trace_b, trace_q;  // EQ_LSX_TRACE=g,b,q: group, first band and first chunk traced
     unsigned long long *trace;    // optional event trace (EQ_LSX_TRACE=1): [4 bands][8 events][128 chunks] ns, see dump_lsx_stats
@@ -614,15 +616,12 @@ struct TbxJob {
 };
 
 __global__ void __launch_bounds__(TBX_THREADS, 5) k_linsolve_tb(const TbxParams p) {
+    if (p.run_if && *p.run_if == 0u) return;
     EQ_DYN_SMEM(tbx_smem_raw);
     const uint32_t sbase = smem_u32(tbx_smem_raw);
     const int total = p.njobs * p.nprob;
     const int lane = (int)threadIdx.x & 31;
-    if (threadIdx.x == 0) {
-        sts_u32(sbase + TBX_MISC_OFF + 8u, (p.rotate_roles && !TBX_SPLIT) ? eq_cta_slot_rotation() : 0u);
-        for (int i = 0; i < 3 * TBX_SLOTS; ++i) mbar_init(sbase + TBX_BAR_OFF + (uint32_t)i * 16u, 1u);
-        mbar_init(sbase + TBX_AB_OFF, 1u);
-    }
+    if (threadIdx.x == 0) sts_u32(sbase + TBX_MISC_OFF + 8u, (p.rotate_roles && !TBX_SPLIT) ? eq_cta_slot_rotation() : 0u);
     __syncthreads();
     // role 0 compute, 1 loader, 2 storer, 3 publisher (uniform per warp: taken through a shuffle so that
     // the compiler keeps the dispatch branch-uniform)
@@ -635,8 +634,7 @@ __global__ void __launch_bounds__(TBX_THREADS, 5) k_linsolve_tb(const TbxParams 
             const unsigned t = (ld_volatile_s32(p.error) != 0) ? 0xffffffffu : atomicAdd(p.ticket, 1u);
             sts_u32(sbase + TBX_MISC_OFF, t);
             sts_u32(sbase + TBX_MISC_OFF + 4u, 0u);
-            for (int i = 0; i < 3 * TBX_SLOTS; ++i) mbar_inval(sbase + TBX_BAR_OFF + (uint32_t)i * 16u);   // see mbar_inval
-            mbar_inval(sbase + TBX_AB_OFF);
+            // (re-initialised per job: only sound while a job completes an even number of phases per slot, see single_shot)
             for (int i = 0; i < TBX_SLOTS; ++i) {
                 mbar_init(sbase + TBX_BAR_OFF + (uint32_t)i * 16u, 32u);
                 mbar_init(sbase + TBX_BAR_OFF + (uint32_t)(TBX_SLOTS + i) * 16u, 1u);
@@ -674,5 +672,6 @@ __global__ void __launch_bounds__(TBX_THREADS, 5) k_linsolve_tb(const TbxParams 
 #undef TBX_DISPATCH
         __syncthreads();
         if (p.jobtimes && threadIdx.x == 0 && pi == 0) p.jobtimes[4 * ((size_t)g * p.NBP + b) + 2] = lsx_gtime();
+        if (p.single_shot) break;
     }
 }

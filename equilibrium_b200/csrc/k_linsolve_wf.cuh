@@ -117,6 +117,7 @@ struct WfParams {
     int *error;
     int pub_batch;
     int rotate_roles;
+    const unsigned *run_if;      // not null: return at once when *run_if == 0 (see LsxParams::run_if)
     int force_general;           // EQ_WF_GENERAL=1: every macro step takes the general loop (tests)
     int debug_nodeps;            // -DEQ_DEBUG_KNOBS builds only
     unsigned long long *jobtimes; // EQ_WF_JOBTIMES=file: [njobs][4] ns: ticket taken, first flags seen, first wave landed, compute done
@@ -628,6 +629,7 @@ struct WfJob {
 #define WF_CTAS_PER_SM 4
 #endif
 __global__ void __launch_bounds__(WF_THREADS, WF_CTAS_PER_SM) k_linsolve_wf(const WfParams p) {
+    if (p.run_if && *p.run_if == 0u) return;
     EQ_DYN_SMEM(wf_smem_raw);
     const uint32_t sbase = smem_u32(wf_smem_raw);
     const int total = p.njobs * p.nprob;

@@ -100,4 +100,12 @@ extern "C" {
     pub fn eq_render_rgba(h: *mut eq_fluid, colors: *const EqColors, host_rgba: *mut c_void, bytes: usize) -> c_int;
     pub fn eq_host_alloc(out: *mut *mut c_void, bytes: usize) -> c_int;
     pub fn eq_host_free(p: *mut c_void) -> c_int;
+    // row slabs over several GPUs: one handle per device, see CudaFluidGroup
+    pub fn eq_upload_rows(h: *mut eq_fluid, field: c_int, row_begin: u32, n_rows: u32, host: *const c_void) -> c_int;
+    pub fn eq_download_rows(h: *mut eq_fluid, field: c_int, row_begin: u32, n_rows: u32, host: *mut c_void) -> c_int;
+    pub fn eq_owned_rows(h: *mut eq_fluid, row_begin: *mut u32, row_end: *mut u32) -> c_int;
+    pub fn eq_ipc_blob_bytes() -> c_int;
+    pub fn eq_ipc_export(h: *mut eq_fluid, blob: *mut c_void, capacity: usize) -> c_int;
+    pub fn eq_ipc_attach(h: *mut eq_fluid, blobs: *const c_void, blob_bytes: usize, world: c_int) -> c_int;
+    pub fn eq_divergence_l2(h: *mut eq_fluid, vx_field: c_int, vy_field: c_int, out: *mut f64) -> c_int;
 }

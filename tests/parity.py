@@ -92,6 +92,33 @@ def check_lin_solve(oracle, lib_path, n, k, rects, orient, a=0.37, seed=0):
     assert bits_equal(got, x), f"lin_solve {ORIENT_NAMES[orient]} N={n} K={k}: {describe_diff(got, x)}"
 
 
+def check_lin_solve_a0(oracle, lib_path, n, k, rects, orient, poison, seed=0, mode="exact"):
+    """lin_solve with a == 0, c == 1 (diffuse with a zero coefficient, fluid.rs:286-297): the library answers with one
+    guarded copy + set_boundaries when every value is finite, moderate and no x0 is -0.0, and falls back to the sweeps
+    otherwise.  `poison` = None (the shortcut applies) or (array, row, col, value): one value that must defeat the guard."""
+    rng = np.random.default_rng(seed)
+    dev, ref = make_pair(oracle, lib_path, n, k, rects, mode=mode)
+    x, x0 = rnd(rng, n), rnd(rng, n)
+    x0[rng.random((n, n)) < 0.1] = 0.0                      # +0.0 is harmless
+    if poison is not None:
+        which, j, i, v = poison
+        (x if which == "x" else x0)[j, i] = np.float32(v)
+    dev.upload("velocities_x", x)
+    dev.upload("velocities_x0", x0)
+    dev.op_lin_solve(orient, "velocities_x", "velocities_x0", 0.0, 1.0, k)
+    if mode == "exact":
+        oracle.lin_solve(orient, x, x0, 0.0, 1.0, k, ref.cells)
+    else:
+        oracle.lin_solve(orient, x, x0, 0.0, 1.0, k, ref.cells, red_black=True)
+    got = dev.download("velocities_x")
+    nan_both = np.isnan(got) & np.isnan(x)                  # NaN payloads are not compared (x86 vs GPU quiet-NaN patterns)
+    assert np.array_equal(np.isnan(got), np.isnan(x)), "NaN cells differ"
+    g, w = got.copy(), x.copy()
+    g[nan_both] = 0.0
+    w[nan_both] = 0.0
+    assert bits_equal(g, w), f"lin_solve a=0 {ORIENT_NAMES[orient]} N={n} K={k} poison={poison}: {describe_diff(g, w)}"
+
+
 def check_project(oracle, lib_path, n, k, rects, seed=0):
     rng = np.random.default_rng(seed)
     dev, ref = make_pair(oracle, lib_path, n, k, rects)

@@ -75,6 +75,59 @@ def test_rust_sys_crate_binds_only_declared_symbols():
         assert needed in bound, needed
 
 
+C2RUST = {"int": "c_int", "uint32_t": "u32", "int64_t": "i64", "float": "f32", "double": "f64", "size_t": "usize",
+          "void": "c_void", "char": "c_char", "eq_fluid": "eq_fluid", "EqParams": "EqParams", "EqSource": "EqSource",
+          "EqNoise": "EqNoise", "EqColors": "EqColors", "EqProfile": "EqProfile"}
+
+
+def _c_type_to_rust(ctype):
+    t = ctype.strip()
+    stars = t.count("*")
+    const = "const" in t
+    base = t.replace("const", "").replace("*", "").strip()
+    r = C2RUST[base]
+    if stars == 0:
+        return r
+    if stars == 1:
+        return ("*const " if const else "*mut ") + r
+    return "*mut *mut " + r
+
+
+def test_rust_extern_signatures_match_the_header():
+    """Every `pub fn eq_*` of the -sys crate against the prototype the header declares: same arity, every argument and the
+    return value the Rust spelling of the C type (the crates cannot be compiled here, so this is the type check)."""
+    hdr = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    protos = {}
+    for ret, name, args in re.findall(r"^\s*((?:const\s+)?\w+\s*\**)\s*(eq_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", hdr, flags=re.M):
+        alist = [] if args.strip() in ("void", "") else [a.strip() for a in args.split(",")]
+        types = []
+        for a in alist:
+            m = re.match(r"(.*?)(\w+)$", a)              # strip the parameter name
+            types.append(_c_type_to_rust(m.group(1)))
+        protos[name] = (_c_type_to_rust(ret), types)
+    rs = open(os.path.join(ROOT, "rust", "equilibrium-cuda-sys", "src", "lib.rs")).read()
+    ext = rs[rs.index('extern "C"'):]
+    checked = 0
+    for name, args, ret in re.findall(r"pub fn (eq_[a-z0-9_]+)\s*\(([^)]*)\)\s*(?:->\s*([^;]+))?;", ext, flags=re.S):
+        want_ret, want_args = protos[name]
+        got_args = [re.sub(r"\s+", " ", a.split(":", 1)[1].strip()) for a in args.split(",") if ":" in a]
+        assert got_args == want_args, (name, got_args, want_args)
+        assert re.sub(r"\s+", " ", (ret or "()").strip()) == want_ret, (name, ret, want_ret)
+        checked += 1
+    assert checked >= 34
+
+
+def test_rust_wrapper_covers_the_reference_surface():
+    """CudaFluid has a method for every entry the reference's callers use plus Default's double init."""
+    rs = open(os.path.join(ROOT, "rust", "equilibrium-cuda", "src", "lib.rs")).read()
+    for needed in ("pub fn new(", "pub fn with_mode(", "pub fn init_default(", "pub fn set_params(", "pub fn add_density(",
+                   "pub fn add_velocity(", "pub fn reset_walls(", "pub fn step(", "pub fn step_n(", "pub fn fill_rect(",
+                   "impl Default for CudaFluid", "impl Clone for CudaFluid", "impl Drop for CudaFluid", "pub struct CudaFluidGroup"):
+        assert needed in rs, needed
+    default_impl = rs[rs.index("impl Default for CudaFluid"):]
+    assert "init_default()" in default_impl[:600]          # fluid.rs:83-89: new() then init() again
+
+
 def test_colors_layout_matches_header():
     assert C.sizeof(_lib.EqColors) == 12 and _lib.SNAPSHOT_SLOTS == 2
 

@@ -55,6 +55,22 @@ def test_lin_solve_exact_fast_and_general_macro_steps(oracle, emu_lib, orient):
     P.check_lin_solve(oracle, emu_lib, 168, 2, [(100, 70, 108, 101)], orient)
 
 
+A0_POISONS = [None, ("x0", 20, 30, -0.0), ("x0", 5, 5, float("nan")), ("x", 0, 7, float("inf")), ("x", 40, 41, -3e38),
+              ("x0", 1, 1, 2e37), ("x", 63, 63, float("nan"))]
+
+
+@pytest.mark.parametrize("orient", [P.ROW, P.COL, P.PASSIVE])
+@pytest.mark.parametrize("poison", A0_POISONS)
+def test_lin_solve_zero_coefficient_shortcut_and_its_guard(oracle, emu_lib, orient, poison):
+    # the reference's default diffusion is 0 (configs.rs:50-60): a = 0, c = 1
+    P.check_lin_solve_a0(oracle, emu_lib, 64, 3, RECTS64, orient, poison)
+
+
+def test_lin_solve_zero_coefficient_red_black(oracle, emu_lib):
+    P.check_lin_solve_a0(oracle, emu_lib, 70, 5, [(10, 10, 30, 20)], P.PASSIVE, None, mode="red_black")
+    P.check_lin_solve_a0(oracle, emu_lib, 70, 5, [(10, 10, 30, 20)], P.PASSIVE, ("x0", 33, 21, -0.0), mode="red_black")
+
+
 def test_lin_solve_zero_iterations_is_a_no_op(oracle, emu_lib):
     P.check_lin_solve(oracle, emu_lib, 32, 0, [], P.ROW)
 

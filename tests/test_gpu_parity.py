@@ -40,6 +40,19 @@ def test_lin_solve_full_row_and_column_walls(oracle, cuda_lib):
         P.check_set_boundaries(oracle, cuda_lib, n, rects, orient)
 
 
+@pytest.mark.parametrize("orient", [P.ROW, P.COL, P.PASSIVE])
+@pytest.mark.parametrize("poison", [None, ("x0", 200, 300, -0.0), ("x0", 5, 5, float("nan")), ("x", 0, 7, float("inf")),
+                                    ("x", 400, 41, -3e38), ("x0", 1, 1, 2e37)])
+def test_lin_solve_zero_coefficient_shortcut_and_its_guard(oracle, cuda_lib, orient, poison):
+    # a = 0, c = 1 (the reference's default diffusion, configs.rs:50-60): guarded copy, or the sweeps when the guard fails
+    P.check_lin_solve_a0(oracle, cuda_lib, 512, 6, P.random_rects(512, 8, 3), orient, poison)
+
+
+def test_lin_solve_zero_coefficient_red_black(oracle, cuda_lib):
+    P.check_lin_solve_a0(oracle, cuda_lib, 700, 9, P.random_rects(700, 8, 5), P.PASSIVE, None, mode="red_black")
+    P.check_lin_solve_a0(oracle, cuda_lib, 700, 9, P.random_rects(700, 8, 5), P.PASSIVE, ("x0", 333, 21, -0.0), mode="red_black")
+
+
 def test_lin_solve_more_iterations_than_one_launch(oracle, cuda_lib):
     # > LSX_KMAX (256) iterations are split over several wavefront launches
     P.check_lin_solve(oracle, cuda_lib, 64, 300, [(10, 10, 30, 20)], P.COL)
