@@ -142,7 +142,7 @@ struct eq_fluid {
     unsigned *peer_sync[EQ_MAX_RANKS];
     bool peer_ipc[EQ_MAX_RANKS];                 // mapped with cudaIpcOpenMemHandle (must be closed)
     unsigned *sync;                              // my cross-GPU sync slots
-    unsigned halo_epoch, bar_epoch, rb_epoch;
+    unsigned halo_epoch, bar_epoch, rb_epoch, or_epoch;
     bool attached;
     // per-frame snapshots: staging slots, their events, the copy stream
     cudaStream_t copy_stream;
@@ -242,6 +242,7 @@ static int halo_xchg_buf(eq_fluid *h, float *buf, float *up, float *down, int nr
     a.epoch = ++h->halo_epoch;
     a.nrows = nrows;
     a.error = reinterpret_cast<int *>(h->flags + 1);
+    a.run_if = h->run_if;
     EQ_LAUNCH(k_halo_exchange, 2, 1024, 16, h->stream, a, h->L);
     return check_launch("k_halo_exchange");
 }
@@ -850,7 +851,7 @@ static int lin_solve_dispatch(eq_fluid *h, const LinSolveReq *req, int nreq, int
 // a == 0, c == 1 (k_a0_check in k_stencils.cuh): guard, copy, the solver behind the guard's flag, one set_boundaries.
 static bool a0_shortcut_applies(const eq_fluid *h, const LinSolveReq &r) {
     static const bool off = getenv("EQ_A0_FASTPATH") && atoi(getenv("EQ_A0_FASTPATH")) == 0;
-    return !off && h->world == 1 && r.a == 0.0f && !std::signbit(r.a) && r.c == 1.0f;
+    return !off && r.a == 0.0f && !std::signbit(r.a) && r.c == 1.0f;
 }
 
 static int lin_solve_a0(eq_fluid *h, const LinSolveReq &r, int slot, int64_t iters) {
@@ -859,9 +860,22 @@ static int lin_solve_a0(eq_fluid *h, const LinSolveReq &r, int slot, int64_t ite
     {
         ProfScope ps(h, CAT_OTHER, 2);
         CU(cudaMemsetAsync(flag, 0, sizeof(unsigned), h->stream));
-        const dim3 grid((unsigned)((L.N + 4 * 256 - 1) / (4 * 256)), (unsigned)std::min(L.N, 2048), 1);
+        const dim3 grid((unsigned)((L.N + 4 * 256 - 1) / (4 * 256)), (unsigned)std::min(L.row1 - L.row0, 2048), 1);
         EQ_LAUNCH(k_a0_check, grid, 256, 0, h->stream, r.x, r.x0, flag, L);
         TRY(check_launch("k_a0_check"));
+        if (h->world > 1) {                                   // every rank must come to the same decision
+            TRY(need_attached(h));
+            EqBarrierArgs a;
+            memset(&a, 0, sizeof(a));
+            a.sync = h->sync;
+            for (int q = 0; q < h->world; ++q) a.peer_sync[q] = h->peer_sync[q];
+            a.rank = h->rank;
+            a.world = h->world;
+            a.epoch = ++h->or_epoch;
+            a.error = reinterpret_cast<int *>(h->flags + 1);
+            EQ_LAUNCH(k_flag_or_all, 1, 32, 0, h->stream, a, flag);
+            TRY(check_launch("k_flag_or_all"));
+        }
         EQ_LAUNCH(k_a0_apply, grid, 256, 0, h->stream, r.x, r.x0, flag, L);
         TRY(check_launch("k_a0_apply"));
     }
@@ -869,7 +883,8 @@ static int lin_solve_a0(eq_fluid *h, const LinSolveReq &r, int slot, int64_t ite
     const int rc = lin_solve_dispatch(h, &r, 1, iters);     // returns at once on the device unless the guard failed
     h->run_if = nullptr;
     TRY(rc);
-    return set_boundaries(h, r.orient, r.x);                 // idempotent after a real solve
+    TRY(set_boundaries(h, r.orient, r.x));                   // idempotent after a real solve (refreshes the ghost rows it reads)
+    return halo_xchg(h, r.x);                                // ghost rows for the stencils that follow
 }
 
 static int lin_solve(eq_fluid *h, const LinSolveReq *req, int nreq, int64_t iters) {

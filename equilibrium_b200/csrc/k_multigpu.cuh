@@ -8,7 +8,7 @@
 #pragma once
 #include "eq_common.cuh"
 
-#define EQ_SYNC_WORDS 32          // [0..3] halo slots (up A/B, down A/B), [8..15] all-rank barrier
+#define EQ_SYNC_WORDS 32          // [0..3] halo slots (up A/B, down A/B), [8..15] all-rank barrier, [16..31] flag OR (2 x 8)
 #ifdef EQ_HOST_EMU
 #define EQ_XGPU_SPIN_LIMIT (1u << 30)   // emulated ranks are OS threads on a few cores: a spin is a yield, not 100 ns
 #else
@@ -23,6 +23,8 @@ struct EqHaloArgs {
     unsigned epoch;
     int nrows;                    // boundary rows pushed each way (1 for the stencils, 3T for tiled red-black)
     int *error;
+    const unsigned *run_if;       // not null: skip when *run_if == 0 (exchanges that belong to a solve the a == 0 shortcut
+                                  // replaced; the flag is the same on every rank, k_flag_or_all)
 };
 
 __device__ __forceinline__ bool eq_xgpu_wait(const unsigned *slot, unsigned epoch, int *error) {
@@ -46,6 +48,7 @@ __device__ __forceinline__ bool eq_xgpu_wait(const unsigned *slot, unsigned epoc
 // the neighbour's solver may still be patching my boundary row.  Phase B: push my boundary row
 // into the neighbour's ghost row, then "pushed".
 __global__ void __launch_bounds__(1024) k_halo_exchange(EqHaloArgs a, EqLayout L) {
+    if (a.run_if && *a.run_if == 0u) return;
     const int dir = blockIdx.x;
     float *peer = dir == 0 ? a.peer_up : a.peer_down;
     if (!peer) return;
@@ -81,6 +84,30 @@ struct EqBarrierArgs {
     unsigned epoch;
     int *error;
 };
+
+// OR of one flag word over all ranks (the guard of the a == 0 lin_solve shortcut must come out the same everywhere).
+// Rank r stores (epoch << 1 | flag) into slot r of every peer, then waits for every peer's word of this epoch.  Two
+// sets of slots alternate with the epoch: a peer can be at most one reduction ahead of me.
+__global__ void k_flag_or_all(EqBarrierArgs a, unsigned *flag) {
+    const int i = threadIdx.x;
+    const unsigned base = 16u + 8u * (a.epoch & 1u);
+    unsigned mine = *flag != 0u ? 1u : 0u;
+    if (i < a.world && i != a.rank) {
+        __threadfence_system();
+        st_release_sys_u32(a.peer_sync[i] + base + a.rank, (a.epoch << 1) | mine);
+        const unsigned *slot = a.sync + base + i;
+        unsigned spins = 0, v;
+        while (((v = ld_relaxed_sys_u32(slot)) >> 1) < a.epoch) {
+            __nanosleep(100);
+            if ((++spins & 4095u) == 0 && (spins >= EQ_XGPU_SPIN_LIMIT || ld_volatile_s32(a.error) != 0)) {
+                if (spins >= EQ_XGPU_SPIN_LIMIT) *a.error = 4;
+                break;
+            }
+        }
+        v = ld_acquire_sys_u32(slot);
+        if (v & 1u) *flag = 1u;                               // (several threads may store the same 1)
+    }
+}
 
 // All ranks: "everything I launched before this kernel is done" (needed around advect, whose
 // back-trace may read any rank's rows).

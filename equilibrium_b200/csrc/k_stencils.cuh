@@ -115,14 +115,15 @@ __device__ __forceinline__ void eq_corners(float *x, const EqLayout &L) {
 // initial x (the not-yet-updated neighbours of the first sweep, and the frame), or the negation of one of those, so the
 // guard is: all of them finite with |v| <= 1e37 (four of them cannot overflow) and no interior x0 equal to -0.0.
 // k_a0_check raises *flag when the guard fails; k_a0_apply copies x0 into the interior when it did not; the solver
-// kernels are launched regardless and return at once when *flag == 0 (`run_if`).  No host round trip.
+// kernels are launched regardless and return at once when *flag == 0 (`run_if`).  No host round trip.  With row slabs
+// every rank checks the rows it owns and the flags are OR-ed over the ranks (k_flag_or_all) before anybody acts on them.
 // ---------------------------------------------------------------------------
 __global__ void k_a0_check(const float *__restrict__ x, const float *__restrict__ x0, unsigned *flag, EqLayout L) {
     const int N = L.N, P = L.P;
     const int g = (blockIdx.x * blockDim.x + threadIdx.x) * 4;     // 4 columns per thread (float4: P is a multiple of 32)
     if (g >= N) return;
     bool bad = false;
-    for (int j = blockIdx.y; j < N; j += gridDim.y) {
+    for (int j = L.row0 + blockIdx.y; j < L.row1; j += gridDim.y) {   // the rows this rank owns (all of them on one GPU)
         const float4 a = *reinterpret_cast<const float4 *>(x + (size_t)j * P + g);
         const float4 b = *reinterpret_cast<const float4 *>(x0 + (size_t)j * P + g);
         const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
@@ -143,7 +144,7 @@ __global__ void k_a0_apply(float *__restrict__ x, const float *__restrict__ x0, 
     const int N = L.N, P = L.P;
     const int g = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (g >= N) return;
-    for (int j = 1 + blockIdx.y; j <= N - 2; j += gridDim.y) {
+    for (int j = max(L.row0, 1) + blockIdx.y; j <= min(L.row1 - 1, N - 2); j += gridDim.y) {
         float4 v = *reinterpret_cast<const float4 *>(x0 + (size_t)j * P + g);
         if (g >= 4 && g + 3 <= N - 2) {
             *reinterpret_cast<float4 *>(x + (size_t)j * P + g) = v;

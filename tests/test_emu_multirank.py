@@ -161,3 +161,33 @@ def test_device_noise_across_two_slabs(oracle, emu_lib):
     for name, fid in P.F32_FIELDS:
         got, want = assemble(fluids, name), ref.field(fid)
         assert P.bits_equal(got, want), f"{name}: {P.describe_diff(got, want)}"
+
+
+@pytest.mark.parametrize("mode", ["exact", "red_black"])
+@pytest.mark.parametrize("poison_row", [None, 70])
+def test_zero_coefficient_shortcut_across_slabs(oracle, emu_lib, mode, poison_row):
+    """lin_solve with a = 0, c = 1 on three slabs: the guard of the shortcut is OR-ed over the ranks, so a -0.0 in ONE
+    rank's rows (row 70 is the last slab's) must send every rank through the sweeps; without it every rank copies."""
+    world, n, k = 3, 96, 4
+    rects = [(20, 28, 40, 40), (50, 60, 70, 66)]
+    fluids = make_rank_fluids(emu_lib, world, n, k, rects, mode=mode)
+    ref = oracle.RefFluid(n, 0.02, k)
+    for r in rects:
+        ref.fill_rect(*r)
+    rng = np.random.default_rng(3)
+    x, x0 = P.rnd(rng, n), P.rnd(rng, n)
+    x0[rng.random((n, n)) < 0.1] = 0.0
+    if poison_row is not None:
+        x0[poison_row, 33] = np.float32(-0.0)
+    for f in fluids:
+        f.upload("velocities_x", x)
+        f.upload("velocities_x0", x0)
+
+    def body(r, barrier):
+        fluids[r].op_lin_solve(P.PASSIVE, "velocities_x", "velocities_x0", 0.0, 1.0, k)
+        fluids[r].sync()
+
+    run_ranks(world, body)
+    oracle.lin_solve(P.PASSIVE, x, x0, 0.0, 1.0, k, ref.cells, red_black=(mode == "red_black"))
+    got = assemble(fluids, "velocities_x")
+    assert P.bits_equal(got, x), P.describe_diff(got, x)
