@@ -238,11 +238,14 @@ def time_device_resident(f, n, steps, warmup, seed, world=1):
     return max_over_ranks(ms, world)
 
 
-RB_ITERS_PER_LAUNCH = 4          # k_rb_reg: RB_T complete iterations of one field per launch
+RB_ITERS_PER_LAUNCH = 4          # k_rb_stream / k_rb_reg: 4 complete iterations of one field per launch
+RB_STREAM_MIN_N = 2048           # eq_api.cu EQ_RB_STREAM_MIN_N: grids from this size on take k_rb_stream
 KERNELS = {
     "exact": "k_linsolve_tb (bit-exact wavefront Gauss-Seidel, 2 iterations fused per job, all K iterations per launch)",
     "exact_slabs": "k_linsolve_exact (row-slab wavefront Gauss-Seidel, all K iterations per launch)",
-    "red_black": "k_rb_reg (red-black Gauss-Seidel, tile in registers, 4 iterations per launch)",
+    "red_black": "k_rb_stream (red-black Gauss-Seidel, one warp per 104-column strip sliding down the rows, rows brought in by "
+                 "bulk copies, 4 iterations per launch)",
+    "red_black_small": "k_rb_reg (red-black Gauss-Seidel, tile in registers, 4 iterations per launch)",
 }
 PHASES = ["lin_solve_ms", "advect_ms", "project_ms", "boundary_ms", "other_ms"]
 
@@ -296,7 +299,7 @@ def measure_mode(wl, wl_key, mode, steps, warmup, local_rank, rank, world, peak,
     ls_s = prof["lin_solve_ms"] * 1e-3
     if mode == "red_black":
         launches = max(1, solves * ((k + RB_ITERS_PER_LAUNCH - 1) // RB_ITERS_PER_LAUNCH))
-        kernel, tkey = KERNELS["red_black"], "rb_dram_bytes_per_launch"
+        kernel, tkey = KERNELS["red_black" if n >= RB_STREAM_MIN_N else "red_black_small"], "rb_dram_bytes_per_launch"
     else:
         launches = max(1, solves)
         kernel, tkey = (KERNELS["exact"] if world == 1 else KERNELS["exact_slabs"]), "dram_bytes_per_launch"

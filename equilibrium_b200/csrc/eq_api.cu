@@ -18,6 +18,7 @@
 #include "k_linsolve_tb.cuh"
 #include "k_linsolve_wf.cuh"
 #include "k_linsolve_rb.cuh"
+#include "k_linsolve_rbs.cuh"
 #include "k_stencils.cuh"
 #include "k_multigpu.cuh"
 
@@ -618,6 +619,9 @@ static int lin_solve_exact_tb(eq_fluid *h, const LinSolveReq *req, int nreq, int
     return EQ_OK;
 }
 
+#ifndef EQ_RB_STREAM_MIN_N
+#define EQ_RB_STREAM_MIN_N 2048   // C3 (4096^2): k_rb_stream 1.47 ms / solve, k_rb_slide 2.14, k_rb_reg 2.30; C2 (1024^2): k_rb_reg 0.32 ms
+#endif
 #ifndef EQ_DEFAULT_EXACT_WF
 #define EQ_DEFAULT_EXACT_WF 0   // until k_linsolve_wf beats k_linsolve_tb on the BASELINE configs
 #endif
@@ -770,7 +774,135 @@ static int peer_buffer(eq_fluid *h, const float *mine, int r, float **out) {
     return EQ_OK;
 }
 
+// Sliding-window red-black kernel (k_linsolve_rbs.cuh): RS_T iterations per pass, ping-pong between x and rb_tmp.
+static int lin_solve_red_black_slide(eq_fluid *h, const LinSolveReq *req, int nreq, int64_t iters) {
+    const EqLayout L = h->L;
+    const int rows = L.row1 - L.row0;
+    // a task (one warp) = a strip of RS_SW columns x a segment of rows; segments as long as possible (each recomputes
+    // 2 RS_VH rows) but enough of them to give every SM ~16 warps
+    const int nstrips = (L.N + RS_SW - 1) / RS_SW;
+    const int want_segs = std::max(1, (16 * h->sm_count + nstrips - 1) / nstrips);
+    const int seg_rows = std::min(RS_SEG, std::max(32, (rows + want_segs - 1) / want_segs));
+    const int nsegs = (rows + seg_rows - 1) / seg_rows;
+    const int grid = (nstrips * nsegs + RS_WARPS - 1) / RS_WARPS;
+    for (int i = 0; i < nreq; ++i) {
+        const float c_recip = 1.0f / req[i].c;
+        float *cur = req[i].x, *other = h->rb_tmp;
+        TRY(halo_xchg(h, const_cast<float *>(req[i].x0), RB_H));    // the first / last segment recomputes RS_VH ghost rows
+        for (int64_t done = 0; done < iters; done += RS_T) {
+            const int it = (int)std::min<int64_t>(RS_T, iters - done);
+            TRY(halo_xchg(h, cur, RB_H));                           // ghost rows of the current iterate (also the neighbour barrier)
+            EQ_LAUNCH(k_rb_slide, grid, RS_THREADS, 0, h->stream, cur, other, req[i].x0, h->codes, h->chunk_flags, req[i].a,
+                      c_recip, req[i].orient, it, L.row0, L.row1, nstrips, nsegs, seg_rows, h->run_if, L);
+            TRY(check_launch("k_rb_slide"));
+            std::swap(cur, other);
+        }
+        if (cur != req[i].x) {
+            if (h->run_if) {      // the launches above may have been skipped (a == 0 shortcut): then `cur` holds nothing
+                const dim3 g((unsigned)((L.P / 4 + 255) / 256), (unsigned)std::min(rows, 1024), 1);
+                EQ_LAUNCH(k_copy_rows_if, g, 256, 0, h->stream, req[i].x, cur, h->run_if, L.row0, L.row1, L);
+                TRY(check_launch("k_copy_rows_if"));
+            } else {
+                CU(cudaMemcpyAsync(req[i].x + (size_t)L.row0 * L.P, cur + (size_t)L.row0 * L.P,
+                                   (size_t)rows * L.P * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+            }
+        }
+        EQ_LAUNCH(k_corners, 1, 32, 0, h->stream, req[i].x, L);
+        TRY(check_launch("k_corners"));
+        TRY(halo_xchg(h, req[i].x));
+    }
+    return EQ_OK;
+}
+
+// Streaming red-black kernel (k_rb_stream): RQ_T iterations per pass, rows brought in by bulk copies; what is left of
+// `iters` after the last full pass goes through k_rb_slide (2 or 1 iterations per pass).
+static int lin_solve_red_black_stream(eq_fluid *h, const LinSolveReq *req, int nreq, int64_t iters) {
+    const EqLayout L = h->L;
+    const int rows = L.row1 - L.row0;
+    // k_rb_stream: a task (one warp) = a strip of RQ_SW columns x a segment of rows.  Every segment recomputes
+    // 2 RQ_VH rows and fills its window (13 rows); tasks run in waves of `slots` warps: take the segment count with the
+    // smallest (waves x rows per task), the larger count on a tie (smoother tail).  The strips that touch the left /
+    // right wall run range tests and set_boundaries on every row (~3x the time per row): quarter-length segments.
+    const int nstrips = (L.N + RQ_SW - 1) / RQ_SW;
+    int n_edge = 1;
+    for (int sx = nstrips - 1; sx >= 1 && sx * RQ_SW - RQ_HALO + 127 > L.N - 2; --sx) ++n_edge;
+    n_edge = std::min(n_edge, nstrips);
+    const int ns = nstrips - n_edge;
+    const int slots = h->sm_count * RQ_CTAS_PER_SM;
+    int nsegs = 1;
+    auto edge_rows = [&](int sr) { return std::min(rows, std::max(64, sr / 4)); };
+    {
+        double best = 1e300;
+        for (int s = 1; s <= std::max(1, rows / 64); ++s) {
+            const int sr = (rows + s - 1) / s, se = edge_rows(sr);
+            const long long tasks = (long long)ns * s + (long long)n_edge * ((rows + se - 1) / se);
+            const double cost = (double)((tasks + slots - 1) / slots) * (sr + 2 * RQ_VH + 13);
+            if (cost <= best * 1.02) {
+                best = std::min(best, cost);
+                nsegs = s;
+            }
+        }
+        nsegs = env_int("EQ_RQ_SEGS", nsegs);
+    }
+    const int seg_rows = (rows + nsegs - 1) / nsegs;
+    nsegs = (rows + seg_rows - 1) / seg_rows;
+    const int seg_rows_e = edge_rows(seg_rows), nsegs_e = (rows + seg_rows_e - 1) / seg_rows_e;
+    const int grid = n_edge * nsegs_e + ns * nsegs;
+    // k_rb_slide for the remainder
+    const int nstrips2 = (L.N + RS_SW - 1) / RS_SW;
+    const int want_segs = std::max(1, (16 * h->sm_count + nstrips2 - 1) / nstrips2);
+    const int seg_rows2 = std::min(RS_SEG, std::max(32, (rows + want_segs - 1) / want_segs));
+    const int nsegs2 = (rows + seg_rows2 - 1) / seg_rows2;
+    const int grid2 = (nstrips2 * nsegs2 + RS_WARPS - 1) / RS_WARPS;
+    for (int i = 0; i < nreq; ++i) {
+        const float c_recip = 1.0f / req[i].c;
+        float *cur = req[i].x, *other = h->rb_tmp;
+        TRY(halo_xchg(h, const_cast<float *>(req[i].x0), RB_H));    // the first / last segment recomputes ghost rows
+        int64_t done = 0;
+        while (done < iters) {
+            TRY(halo_xchg(h, cur, RB_H));                           // ghost rows of the current iterate (also the neighbour barrier)
+            if (iters - done >= RQ_T) {
+                EQ_LAUNCH(k_rb_stream, grid, RQ_THREADS, RQ_SMEM_BYTES, h->stream, cur, other, req[i].x0, h->codes, h->chunk_flags,
+                          req[i].a, c_recip, req[i].orient, L.row0, L.row1, nstrips, n_edge, nsegs, seg_rows, nsegs_e, seg_rows_e,
+                          h->run_if, L);
+                TRY(check_launch("k_rb_stream"));
+                done += RQ_T;
+            } else {
+                const int it = (int)std::min<int64_t>(RS_T, iters - done);
+                EQ_LAUNCH(k_rb_slide, grid2, RS_THREADS, 0, h->stream, cur, other, req[i].x0, h->codes, h->chunk_flags, req[i].a,
+                          c_recip, req[i].orient, it, L.row0, L.row1, nstrips2, nsegs2, seg_rows2, h->run_if, L);
+                TRY(check_launch("k_rb_slide"));
+                done += it;
+            }
+            std::swap(cur, other);
+        }
+        if (cur != req[i].x) {
+            if (h->run_if) {      // the launches above may have been skipped (a == 0 shortcut): then `cur` holds nothing
+                const dim3 g((unsigned)((L.P / 4 + 255) / 256), (unsigned)std::min(rows, 1024), 1);
+                EQ_LAUNCH(k_copy_rows_if, g, 256, 0, h->stream, req[i].x, cur, h->run_if, L.row0, L.row1, L);
+                TRY(check_launch("k_copy_rows_if"));
+            } else {
+                CU(cudaMemcpyAsync(req[i].x + (size_t)L.row0 * L.P, cur + (size_t)L.row0 * L.P,
+                                   (size_t)rows * L.P * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+            }
+        }
+        EQ_LAUNCH(k_corners, 1, 32, 0, h->stream, req[i].x, L);
+        TRY(check_launch("k_corners"));
+        TRY(halo_xchg(h, req[i].x));
+    }
+    return EQ_OK;
+}
+
 static int lin_solve_red_black(eq_fluid *h, const LinSolveReq *req, int nreq, int64_t iters) {
+    // Grids of EQ_RB_STREAM_MIN_N columns or more: the streaming kernel (one warp per 104-column strip needs >= ~20
+    // strips x a few segments to fill the GPU; below that the register-tile kernel k_rb_reg is faster).
+    // EQ_RB_KERNEL=stream|slide|reg|tiled overrides the choice (A/B runs, emulator tests)
+    {
+        const char *rk = getenv("EQ_RB_KERNEL");
+        const bool fits = (unsigned long long)h->L.N * (unsigned long long)h->L.P < (1ull << 32);   // k_rb_stream: 32-bit element offsets
+        if (fits && (rk ? !strcmp(rk, "stream") : (h->L.N >= EQ_RB_STREAM_MIN_N))) return lin_solve_red_black_stream(h, req, nreq, iters);
+        if (rk && !strcmp(rk, "slide")) return lin_solve_red_black_slide(h, req, nreq, iters);
+    }
     const EqLayout L = h->L;
     const int rows = L.row1 - L.row0;
     // EQ_RB_KERNEL=tiled selects the older shared-memory kernel (A/B runs); the default keeps the tile in registers
@@ -1116,6 +1248,7 @@ static int alloc_handle(const EqParams *params, eq_fluid **out) {
     CU(cudaFuncSetAttribute(k_linsolve_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LSX_SMEM_BYTES));
     CU(cudaFuncSetAttribute(k_rb_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RB_SMEM_BYTES));
     CU(cudaFuncSetAttribute(k_rb_reg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RBR_SMEM_BYTES));
+    CU(cudaFuncSetAttribute(k_rb_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RQ_SMEM_BYTES));
     int per_sm = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_linsolve_exact, LSX_THREADS, LSX_SMEM_BYTES));
     h->lsx_ctas = std::max(1, per_sm) * h->sm_count;

@@ -194,6 +194,27 @@ __device__ __forceinline__ bool mbar_test_wait(uint32_t a, uint32_t parity) {
 __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t a) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(a) : "memory");
 }
+// bulk (TMA, 1-D) copy global -> shared: `bytes`, both addresses multiples of 16; completes `bytes` of the mbarrier's
+// transaction count when the data has landed (SASS UBLKCP)
+__device__ __forceinline__ void bulk_g2s(uint32_t saddr, const void *gmem, uint32_t bytes, uint32_t mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(saddr),
+                 "l"(gmem), "r"(bytes), "r"(mbar)
+                 : "memory");
+}
+// true in exactly one lane of the (converged) warp: the compiler then issues what follows once, without a loop over lanes
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "elect.sync _|P1, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t}"
+        : "=r"(pred));
+    return pred != 0u;
+}
+// one arrival that also announces `bytes` of pending bulk-copy traffic (issued before or after: the count is signed)
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t a, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) {
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }

@@ -63,11 +63,11 @@ __global__ void k_build_codes(const uint8_t *__restrict__ cells, uint8_t *__rest
         const bool owned = (j >= L.row0 && j < L.row1);   // the sparse lists drive stand-alone boundary passes
         if (code & 3u) {
             if (owned) atomicAdd(&counts[0], 1u);
-            chunk_flags[(size_t)((j - 1) / 32) * NC + i / EQ_LSX_CW] = 1;
+            chunk_flags[(size_t)min((j - 1) / 32, NB - 1) * NC + i / EQ_LSX_CW] = 1;
         }
         if (code & 12u) {
             if (owned) atomicAdd(&counts[1], 1u);
-            chunk_flags[(size_t)NB * NC + (size_t)((j - 1) / 32) * NC + i / EQ_LSX_CW] = 1;
+            chunk_flags[(size_t)NB * NC + (size_t)min((j - 1) / 32, NB - 1) * NC + i / EQ_LSX_CW] = 1;
             if (j / 32 < NB)   // row j is also row j0-1 of the band below (cross-band DOWN patch)
                 chunk_flags[(size_t)NB * NC + (size_t)(j / 32) * NC + i / EQ_LSX_CW] = 1;
         }

@@ -47,7 +47,7 @@ def main():
                   "scripts/prof_linsolve.py (Passive solve on the config's grid and rectangles), cold cache"}
     for key, size, k in (("c4", 16384, 20), ("c3", 4096, 40)):
         b, ms = ncu_one("k_linsolve_tb", size, k, 2, "exact", 1)            # launch 0 is the K=1 warm-up
-        rb, rms = ncu_one("k_rb_reg", size, k, 2, "red_black", 1)
+        rb, rms = ncu_one("k_rb_stream", size, k, 2, "red_black", 1)      # (launch 0: the first pass of the first solve)
         rec[key] = {"dram_bytes_per_launch": b, "launch_ms_under_ncu": ms, "rb_dram_bytes_per_launch": rb,
                     "rb_launch_ms_under_ncu": rms, "algorithmic_bytes_per_launch": 12.0 * (size - 2) ** 2 * k,
                     "rb_algorithmic_bytes_per_launch": 12.0 * (size - 2) ** 2 * 4}

@@ -206,6 +206,10 @@ static inline bool mbar_try_wait(uint32_t a, uint32_t parity) {
 }
 static inline bool mbar_test_wait(uint32_t a, uint32_t parity) { return (eq_emu_mb(a)->phase.load(std::memory_order_acquire) & 1u) != parity; }
 static inline void cp_async_mbar_arrive_noinc(uint32_t a) { mbar_arrive(a); }
+// bulk copies land at once; the kernels issue them BEFORE the arrive.expect_tx of their barrier, so the arrival publishes them
+static inline void bulk_g2s(uint32_t saddr, const void *gmem, uint32_t bytes, uint32_t) { memcpy(eq_emu::dyn_smem() + saddr, gmem, bytes); }
+static inline void mbar_arrive_expect_tx(uint32_t a, uint32_t) { mbar_arrive(a); }
+static inline bool elect_one() { return (threadIdx.x & 31u) == 0u; }
 static inline void prefetch_l2(const void *) {}
 static inline void cp_async_commit() {}
 template <int N>

@@ -171,6 +171,28 @@ def test_red_black_tiled_across_tiles(oracle, emu_lib, orient, n):
     assert P.bits_equal(got, x), P.describe_diff(got, x)
 
 
+@pytest.mark.parametrize("kernel", ["slide", "stream"])
+@pytest.mark.parametrize("orient", [P.ROW, P.COL, P.PASSIVE])
+def test_red_black_sliding_window_kernels(oracle, emu_lib, orient, kernel, monkeypatch):
+    # k_rb_slide (2 iterations per pass) and k_rb_stream (4 per pass, rows brought in by bulk copies) are the large-grid
+    # kernels; EQ_RB_KERNEL forces them on a grid small enough for the emulator.  420 columns = 4 / 5 strips, the
+    # rectangles sit in one corner so that interior tasks without mirror codes (no range tests, no set_boundaries),
+    # interior tasks with codes and edge tasks all occur; 11 iterations = two passes of 4, one of 2, one of 1
+    monkeypatch.setenv("EQ_RB_KERNEL", kernel)
+    monkeypatch.setenv("EQ_RQ_SEGS", "4")
+    rng = np.random.default_rng(7)
+    n, k = 420, 11
+    rects = [(300, 40, 330, 90), (310, 300, 318, 380), (2, 200, 9, 203)]
+    dev, ref = P.make_pair(oracle, emu_lib, n, k, rects, mode="red_black")
+    x, x0 = P.rnd(rng, n), P.rnd(rng, n)
+    dev.upload("velocities_x", x)
+    dev.upload("velocities_x0", x0)
+    dev.op_lin_solve(orient, "velocities_x", "velocities_x0", 0.37, 2.48, k)
+    oracle.lin_solve(orient, x, x0, 0.37, 2.48, k, ref.cells, red_black=True)
+    got = dev.download("velocities_x")
+    assert P.bits_equal(got, x), P.describe_diff(got, x)
+
+
 @pytest.mark.parametrize("n,steps", [(64, 1), (101, 0)])      # (the GPU suite runs more frames; emulated steps are slow)
 def test_render_rgba_and_snapshots(oracle, emu_lib, n, steps):
     P.check_render_and_snapshot(oracle, emu_lib, n, [(10, 10, 20, 30), (40, 5, 50, 60)], steps=steps)

@@ -45,6 +45,40 @@ def test_bitwise_against_red_black_restatement(oracle, cuda_lib, orient, n, k):
     assert P.bits_equal(got, x), P.describe_diff(got, x)
 
 
+@pytest.mark.parametrize("orient", [P.ROW, P.COL, P.PASSIVE])
+@pytest.mark.parametrize("n,k", [(2500, 11), (3001, 8)])
+def test_bitwise_large_grid_kernels(oracle, cuda_lib, orient, n, k):
+    # grids of 2048 columns or more take k_rb_stream (4 iterations per pass, k_rb_slide for what is left of K): 25 / 29
+    # strips of 104 columns, several segments, rectangles across the strip and segment seams; 3001 is odd (the last
+    # column quad is half outside the grid)
+    rng = np.random.default_rng(n)
+    dev, ref = P.make_pair(oracle, cuda_lib, n, k, P.random_rects(n, 24, 2), mode="red_black")
+    x, x0 = P.rnd(rng, n), P.rnd(rng, n)
+    dev.upload("velocities_x", x)
+    dev.upload("velocities_x0", x0)
+    dev.op_lin_solve(orient, "velocities_x", "velocities_x0", 0.37, 2.48, k)
+    oracle.lin_solve(orient, x, x0, 0.37, 2.48, k, ref.cells, red_black=True)
+    got = dev.download("velocities_x")
+    assert P.bits_equal(got, x), P.describe_diff(got, x)
+
+
+@pytest.mark.parametrize("kernel", ["stream", "slide", "reg"])
+def test_bitwise_every_kernel_on_one_grid(oracle, cuda_lib, kernel, monkeypatch):
+    # the three red-black kernels are interchangeable: EQ_RB_KERNEL forces each of them on the same 1500^2 problem
+    monkeypatch.setenv("EQ_RB_KERNEL", kernel)
+    n, k = 1500, 7
+    rng = np.random.default_rng(5)
+    dev, ref = P.make_pair(oracle, cuda_lib, n, k, P.random_rects(n, 12, 3), mode="red_black")
+    for orient in (P.ROW, P.COL, P.PASSIVE):
+        x, x0 = P.rnd(rng, n), P.rnd(rng, n)
+        dev.upload("velocities_x", x)
+        dev.upload("velocities_x0", x0)
+        dev.op_lin_solve(orient, "velocities_x", "velocities_x0", 0.37, 2.48, k)
+        oracle.lin_solve(orient, x, x0, 0.37, 2.48, k, ref.cells, red_black=True)
+        got = dev.download("velocities_x")
+        assert P.bits_equal(got, x), P.describe_diff(got, x)
+
+
 @pytest.mark.parametrize("n,k", [(128, 16), (512, 20)])
 def test_tolerance_against_lexicographic_reference(oracle, cuda_lib, n, k):
     dev, ref = P.make_pair(oracle, cuda_lib, n, k, P.random_rects(n, 4, n), mode="red_black")
