@@ -619,6 +619,9 @@ static int lin_solve_exact_tb(eq_fluid *h, const LinSolveReq *req, int nreq, int
     return EQ_OK;
 }
 
+#ifndef RQ_SEG_ROWS
+#define RQ_SEG_ROWS 192           // rows per k_rb_stream task (see lin_solve_red_black_stream)
+#endif
 #ifndef EQ_RB_STREAM_MIN_N
 #define EQ_RB_STREAM_MIN_N 2048   // C3 (4096^2): k_rb_stream 1.47 ms / solve, k_rb_slide 2.14, k_rb_reg 2.30; C2 (1024^2): k_rb_reg 0.32 ms
 #endif
@@ -820,30 +823,20 @@ static int lin_solve_red_black_stream(eq_fluid *h, const LinSolveReq *req, int n
     const EqLayout L = h->L;
     const int rows = L.row1 - L.row0;
     // k_rb_stream: a task (one warp) = a strip of RQ_SW columns x a segment of rows.  Every segment recomputes
-    // 2 RQ_VH rows and fills its window (13 rows); tasks run in waves of `slots` warps: take the segment count with the
-    // smallest (waves x rows per task), the larger count on a tie (smoother tail).  The strips that touch the left /
-    // right wall run range tests and set_boundaries on every row (~3x the time per row): quarter-length segments.
+    // 2 RQ_VH rows and fills its window (13 rows), so long segments waste less -- but the tasks differ in cost (rows with
+    // mirror codes run set_boundaries, ~2x the time) and the hardware balances them only when there are several waves of
+    // them: measured at 16384^2 (2368 warps resident), segments of 1171 / 585 / 293 / 195 rows give 3.66 / 3.59 /
+    // 3.50 / 3.43 ms per Passive solve and 5.45 / 4.92 / 4.26 / 4.12 ms per AdjustRow solve (16 rectangles); at 4096^2
+    // 195 rows is the best as well.  The strips that touch the left / right wall run range tests and
+    // set_boundaries on every row (~3x the time per row): quarter-length segments, launched first.
     const int nstrips = (L.N + RQ_SW - 1) / RQ_SW;
     int n_edge = 1;
     for (int sx = nstrips - 1; sx >= 1 && sx * RQ_SW - RQ_HALO + 127 > L.N - 2; --sx) ++n_edge;
     n_edge = std::min(n_edge, nstrips);
     const int ns = nstrips - n_edge;
-    const int slots = h->sm_count * RQ_CTAS_PER_SM;
-    int nsegs = 1;
     auto edge_rows = [&](int sr) { return std::min(rows, std::max(64, sr / 4)); };
-    {
-        double best = 1e300;
-        for (int s = 1; s <= std::max(1, rows / 64); ++s) {
-            const int sr = (rows + s - 1) / s, se = edge_rows(sr);
-            const long long tasks = (long long)ns * s + (long long)n_edge * ((rows + se - 1) / se);
-            const double cost = (double)((tasks + slots - 1) / slots) * (sr + 2 * RQ_VH + 13);
-            if (cost <= best * 1.02) {
-                best = std::min(best, cost);
-                nsegs = s;
-            }
-        }
-        nsegs = env_int("EQ_RQ_SEGS", nsegs);
-    }
+    int nsegs = std::max(1, (rows + RQ_SEG_ROWS / 2) / RQ_SEG_ROWS);
+    nsegs = env_int("EQ_RQ_SEGS", nsegs);
     const int seg_rows = (rows + nsegs - 1) / nsegs;
     nsegs = (rows + seg_rows - 1) / seg_rows;
     const int seg_rows_e = edge_rows(seg_rows), nsegs_e = (rows + seg_rows_e - 1) / seg_rows_e;

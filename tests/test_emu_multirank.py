@@ -133,6 +133,35 @@ def test_red_black_across_slabs_matches_its_restatement(oracle, emu_lib, world, 
     assert P.bits_equal(got, x), P.describe_diff(got, x)
 
 
+@pytest.mark.parametrize("kernel", ["stream", "slide"])
+@pytest.mark.parametrize("world,n,k", [(2, 200, 9), (3, 260, 6)])
+def test_red_black_large_grid_kernels_across_slabs(oracle, emu_lib, world, n, k, kernel, monkeypatch):
+    # the sliding-window kernels (the default from 2048 columns on) on row slabs: every pass starts with the exchange of
+    # 12 ghost rows, segments at a slab edge recompute the neighbour's rows
+    monkeypatch.setenv("EQ_RB_KERNEL", kernel)
+    monkeypatch.setenv("EQ_RQ_SEGS", "2")
+    rects = [(10, 40, 60, 70), (120, 90, 130, 120)]
+    fluids = make_rank_fluids(emu_lib, world, n, k, rects, mode="red_black")
+    ref = oracle.RefFluid(n, 0.02, k)
+    for r in rects:
+        ref.fill_rect(*r)
+    rng = np.random.default_rng(11)
+    for orient in (P.ROW, P.PASSIVE):
+        x, x0 = P.rnd(rng, n), P.rnd(rng, n)
+        for f in fluids:
+            f.upload("velocities_x", x)
+            f.upload("velocities_x0", x0)
+
+        def body(r, barrier):
+            fluids[r].op_lin_solve(orient, "velocities_x", "velocities_x0", 0.37, 2.48, k)
+            fluids[r].sync()
+
+        run_ranks(world, body)
+        oracle.lin_solve(orient, x, x0, 0.37, 2.48, k, ref.cells, red_black=True)
+        got = assemble(fluids, "velocities_x")
+        assert P.bits_equal(got, x), P.describe_diff(got, x)
+
+
 def test_unattached_handle_refuses_to_step(emu_lib):
     from equilibrium_b200 import EquilibriumError
     f = Fluid(FluidConfigs(), SimulationConfigs(0.02, 1, 96), lib_path=emu_lib, rank=0, world=2)
