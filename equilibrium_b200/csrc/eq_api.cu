@@ -619,8 +619,48 @@ static int lin_solve_exact_tb(eq_fluid *h, const LinSolveReq *req, int nreq, int
     return EQ_OK;
 }
 
+// Exact mode on row slabs, plan "replica": the band-to-band chain of the wavefront solver does not get shorter when
+// the rows are spread over GPUs, and the row-slab kernel is the older one without fused iterations: with 2
+// GPUs a slab solve is much slower than the single-GPU kernel on the whole grid.  So every rank gathers the other
+// slabs of x and x0 over NVLink (direct peer loads, ~2.5 ms per solve at 16384^2 on 2 GPUs) and runs k_linsolve_tb on the
+// whole grid; all ranks end up with the same, complete x, and the stencils around the solve stay slab-parallel.
+// Measured C4 frame: 77.8 ms on 2 GPUs (slabs 96.8; one GPU 72.1), 88.5 ms on 4 (slabs 68): the default for 2 ranks only.
+static int lin_solve_exact_replica(eq_fluid *h, const LinSolveReq *req, int nreq, int64_t iters) {
+    TRY(need_attached(h));
+    const EqLayout L = h->L;
+    {
+        ProfScope ps(h, CAT_OTHER, 2 + 2 * nreq * (h->world - 1));
+        TRY(barrier_all(h));                                    // every slab of x and x0 is final
+        const EqPeerTable t = peer_table(h, req[0].x);          // (row partition)
+        for (int i = 0; i < nreq; ++i) {
+            const float *src[2] = {req[i].x, req[i].x0};
+            for (int q = 0; q < h->world; ++q) {
+                if (q == h->rank) continue;
+                const int r0 = t.row_begin[q], r1 = t.row_begin[q + 1];
+                for (int f = 0; f < 2; ++f) {
+                    const int fi = field_index(h, src[f]);
+                    if (fi < 0) return eq_fail(EQ_ERR_INVALID, "replicated solve of an unknown field");
+                    const dim3 g((unsigned)((L.P / 4 + 255) / 256), (unsigned)std::min(r1 - r0, 1024), 1);
+                    EQ_LAUNCH(k_copy_rows_if, g, 256, 0, h->stream, h->f[fi], h->peer_f[q][fi], h->run_if, r0, r1, L);
+                    TRY(check_launch("k_copy_rows_if"));
+                }
+            }
+        }
+        TRY(barrier_all(h));                                    // nobody overwrites rows that a peer is still reading
+    }
+    const EqLayout mine = h->L;
+    h->L.row0 = 0;
+    h->L.row1 = L.N;
+    const int rc = lin_solve_exact_tb(h, req, nreq, iters);
+    h->L = mine;
+    return rc;
+}
+
 #ifndef RQ_SEG_ROWS
 #define RQ_SEG_ROWS 192           // rows per k_rb_stream task (see lin_solve_red_black_stream)
+#endif
+#ifndef EQ_EXACT_REPLICA_MAX_WORLD
+#define EQ_EXACT_REPLICA_MAX_WORLD 2   // C4 frame on 2 / 4 / 8 GPUs: slabs 96.8 / 68 / 49.6 ms, replicated solve 77.8 / 88.5 / - (the gather grows with the ranks)
 #endif
 #ifndef EQ_RB_STREAM_MIN_N
 #define EQ_RB_STREAM_MIN_N 2048   // C3 (4096^2): k_rb_stream 1.47 ms / solve, k_rb_slide 2.14, k_rb_reg 2.30; C2 (1024^2): k_rb_reg 0.32 ms
@@ -1044,6 +1084,10 @@ static int lin_solve_dispatch(eq_fluid *h, const LinSolveReq *req, int nreq, int
     const bool want_wf = ek ? !strcmp(ek, "wf") : (EQ_DEFAULT_EXACT_WF != 0);
     if (h->world == 1 && want_wf && !tb_off) return lin_solve_exact_wf(h, req, nreq, iters);
     if (use_tb) return lin_solve_exact_tb(h, req, nreq, iters);
+    // row slabs: the slab kernel, or every rank solving the whole grid (faster on 2 GPUs; EQ_EXACT_PLAN=slab|replica)
+    const char *plan = getenv("EQ_EXACT_PLAN");
+    const bool replica = plan ? !strcmp(plan, "replica") : (h->world > 1 && h->world <= EQ_EXACT_REPLICA_MAX_WORLD);
+    if (h->world > 1 && replica && TBX_T > 1 && !tb_off) return lin_solve_exact_replica(h, req, nreq, iters);
     return lin_solve_exact(h, req, nreq, iters);
 }
 

@@ -157,9 +157,10 @@ __global__ void k_a0_apply(float *__restrict__ x, const float *__restrict__ x0, 
     }
 }
 
-// copy rows [r0, r1) of src into dst unless *flag == 0 (the red-black ping-pong result is only valid when the solver ran)
+// copy rows [r0, r1) of src into dst unless *flag == 0 (the red-black ping-pong result is only valid when the solver ran;
+// flag == nullptr: always).  src may be a peer's array (the all-gather of the replicated exact solve)
 __global__ void k_copy_rows_if(float *__restrict__ dst, const float *__restrict__ src, const unsigned *__restrict__ flag, int r0, int r1, EqLayout L) {
-    if (*flag == 0u) return;
+    if (flag && *flag == 0u) return;
     const int P = L.P;
     const int g = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (g >= P) return;

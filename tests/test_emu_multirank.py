@@ -56,8 +56,10 @@ def assemble(fluids, name):
     return out
 
 
+@pytest.mark.parametrize("plan", ["slab", "replica"])
 @pytest.mark.parametrize("world,n,k", [(2, 96, 3), (3, 130, 2)])
-def test_steps_match_single_domain_oracle(oracle, emu_lib, world, n, k):
+def test_steps_match_single_domain_oracle(oracle, emu_lib, world, n, k, plan, monkeypatch):
+    monkeypatch.setenv("EQ_EXACT_PLAN", plan)
     rects = [(20, 28, 40, 40), (50, 60, 70, 66), (5, 30, 9, 90)]
     fluids = make_rank_fluids(emu_lib, world, n, k, rects)
     ref = oracle.RefFluid(n, 0.02, k)
@@ -84,8 +86,13 @@ def test_steps_match_single_domain_oracle(oracle, emu_lib, world, n, k):
         assert P.bits_equal(got, want), f"{name}: {P.describe_diff(got, want)}"
 
 
+@pytest.mark.parametrize("plan", ["slab", "replica"])
 @pytest.mark.parametrize("orient", [P.ROW, P.COL, P.PASSIVE])
-def test_lin_solve_across_two_slabs(oracle, emu_lib, orient):
+def test_lin_solve_across_two_slabs(oracle, emu_lib, orient, plan, monkeypatch):
+    # exact mode on row slabs has two plans (eq_api.cu lin_solve_dispatch): the row-slab wavefront kernel, or every rank
+    # gathering the other slabs over peer memory and running the single-GPU kernel on the whole grid (the default up to 4
+    # ranks); each rank only holds its own rows when the solve starts
+    monkeypatch.setenv("EQ_EXACT_PLAN", plan)
     n, k, world = 100, 4, 2
     rects = [(10, 40, 60, 70), (70, 10, 80, 90)]    # straddle the slab boundary (row 65)
     fluids = make_rank_fluids(emu_lib, world, n, k, rects)
