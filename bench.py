@@ -7,17 +7,23 @@ A "step" is one frame of Fluid::step over the whole grid.  metric = grid
 cell-updates/s = size^2 * frames / time (BASELINE.json / SURVEY.md 8d).
 
 Workloads (BASELINE.json configs):
-  c4 (default) 16384^2, 20 GS iterations, 16 random rectangles (seed 16384), exact mode
-  c3           4096^2,  40 GS iterations, 64 random rectangles (seed 4096),  exact mode
+  c4 (default) 16384^2, 20 GS iterations, 16 random rectangles (seed 16384)
+  c3           4096^2,  40 GS iterations, 64 random rectangles (seed 4096)
   c2           1024^2,  20 GS iterations, no obstacles
+  c1           128^2,   100 GS iterations, the reference's default scene (one rectangle)
 The same workload is used for every --gpus value so the driver's scaling series is a
-strong-scaling series (row slabs, halo exchange per sweep).
+strong-scaling series (row slabs, halo exchange per pass).
 
-JSON line keys beyond the base contract: roofline (dominant kernel = the exact lin_solve), cpu_baseline (the CPU
-oracle on one host core, bounded sample), red_black (the red-black mode on the same workload: value, phases and
-its own roofline object), clocks, gpu_launches, e2e (the reference's frame loop through the public API: source
-record in, density frame out through the pinned-memory snapshot path) and e2e_full_mirror (all pub fields up and
-down around every step).
+`value` is the red-black mode (HEADLINE_MODE; bit-identical to the oracle's red-black restatement, tolerance against the
+reference's sweep order measured at c3 / c4 and quoted as red_black.tolerance); --mode exact makes the bit-exact mode the
+headline.  JSON line keys beyond the base contract: headline_mode, roofline (dominant kernel of the headline mode:
+k_rb_stream; `frac` is algorithmic bytes of the streaming model over the measured HBM peak and exceeds 1 because four
+iterations share one pass -- `traffic` / `physical_frac` are the DRAM bytes ncu measured), exact and red_black (each mode
+on the same workload: value, phases and its own roofline object), configs (c3, c2, c1: both modes and a CPU baseline
+each; default run at N=1 only, --no-configs skips them), cpu_baseline (the CPU oracle on one host core, bounded sample,
+"extrapolated" when the sample is a row band), clocks, gpu_launches, e2e (the reference's frame loop through the public
+API: source record in, density frame out through the pinned-memory snapshot path) and e2e_full_mirror (all pub fields up
+and down around every step).
 """
 from __future__ import annotations
 

@@ -21,6 +21,7 @@
 #include "k_linsolve_rbs.cuh"
 #include "k_stencils.cuh"
 #include "k_multigpu.cuh"
+#include "k_linsolve_rbsmall.cuh"
 
 #include <unistd.h>
 
@@ -927,6 +928,26 @@ static int lin_solve_red_black_stream(eq_fluid *h, const LinSolveReq *req, int n
 }
 
 static int lin_solve_red_black(eq_fluid *h, const LinSolveReq *req, int nreq, int64_t iters) {
+    // Grids that fit one SM's shared memory (the reference's 128^2 default scene): one CTA, one launch for all iterations
+    {
+        const char *rk = getenv("EQ_RB_KERNEL");
+        const bool fits = h->world == 1 && (long long)h->L.N * h->L.P <= RBSM_MAX_CELLS && h->L.P / 2 <= RBSM_THREADS &&
+                          (h->L.N + RBSM_THREADS / (h->L.P / 2) - 1) / (RBSM_THREADS / (h->L.P / 2)) <= RBSM_MAXR;
+        if (fits && (rk ? !strcmp(rk, "small") : true) && iters <= 0x7fffffff) {
+            for (int i = 0; i < nreq; ++i) {
+                const size_t smem = (size_t)h->L.N * h->L.P * sizeof(float);
+                const int rg = RBSM_THREADS / (h->L.P / 2);
+                if ((h->L.N + rg - 1) / rg <= 8)
+                    EQ_LAUNCH(k_rb_small<8>, 1, RBSM_THREADS, smem, h->stream, req[i].x, req[i].x0, h->codes, req[i].a,
+                              1.0f / req[i].c, req[i].orient, (int)iters, h->run_if, h->L);
+                else
+                    EQ_LAUNCH(k_rb_small<RBSM_MAXR>, 1, RBSM_THREADS, smem, h->stream, req[i].x, req[i].x0, h->codes, req[i].a,
+                              1.0f / req[i].c, req[i].orient, (int)iters, h->run_if, h->L);
+                TRY(check_launch("k_rb_small"));
+            }
+            return EQ_OK;
+        }
+    }
     // Grids of EQ_RB_STREAM_MIN_N columns or more: the streaming kernel (one warp per 104-column strip needs >= ~20
     // strips x a few segments to fill the GPU; below that the register-tile kernel k_rb_reg is faster).
     // EQ_RB_KERNEL=stream|slide|reg|tiled overrides the choice (A/B runs, emulator tests)
@@ -1286,6 +1307,8 @@ static int alloc_handle(const EqParams *params, eq_fluid **out) {
     CU(cudaFuncSetAttribute(k_rb_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RB_SMEM_BYTES));
     CU(cudaFuncSetAttribute(k_rb_reg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RBR_SMEM_BYTES));
     CU(cudaFuncSetAttribute(k_rb_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RQ_SMEM_BYTES));
+    CU(cudaFuncSetAttribute(k_rb_small<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(RBSM_MAX_CELLS * sizeof(float))));
+    CU(cudaFuncSetAttribute(k_rb_small<RBSM_MAXR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(RBSM_MAX_CELLS * sizeof(float))));
     int per_sm = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_linsolve_exact, LSX_THREADS, LSX_SMEM_BYTES));
     h->lsx_ctas = std::max(1, per_sm) * h->sm_count;

@@ -16,7 +16,7 @@ thread_local Ctx ctx;
 
 Mode mode_for(const char *name) {
     if (strstr(name, "k_linsolve_exact") || strstr(name, "k_linsolve_tb") || strstr(name, "k_linsolve_wf") || strstr(name, "k_halo_exchange")) return CONCURRENT_GRID;
-    if (strstr(name, "k_advect") || strstr(name, "k_divergence_sq") || strstr(name, "k_rb_tiled") || strstr(name, "k_rb_reg") || strstr(name, "k_rb_slide") || strstr(name, "k_rb_stream")) return BLOCK_THREADS;
+    if (strstr(name, "k_advect") || strstr(name, "k_divergence_sq") || strstr(name, "k_rb_tiled") || strstr(name, "k_rb_reg") || strstr(name, "k_rb_slide") || strstr(name, "k_rb_stream") || strstr(name, "k_rb_small")) return BLOCK_THREADS;
     return SEQUENTIAL;
 }
 

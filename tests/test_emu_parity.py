@@ -171,6 +171,25 @@ def test_red_black_tiled_across_tiles(oracle, emu_lib, orient, n):
     assert P.bits_equal(got, x), P.describe_diff(got, x)
 
 
+@pytest.mark.parametrize("n", [24, 101, 128, 160])
+@pytest.mark.parametrize("orient", [P.ROW, P.COL, P.PASSIVE])
+def test_red_black_single_cta_kernel(oracle, emu_lib, orient, n):
+    # grids up to N * P = 32768 cells (the reference's 128^2 default scene) run all K iterations in one launch of one CTA
+    # (k_rb_small): 128 is the 8-rows-per-thread instantiation at its limit, 160 the 16-row one, 101 an odd size with
+    # idle threads in the last row group
+    rng = np.random.default_rng(n)
+    k = 7
+    rects = [(3, 3, 9, 8)] if n < 40 else [(10, 10, 20, 30), (n - 30, 5, n - 12, n - 8), (40, n - 4, 60, n - 2)]
+    dev, ref = P.make_pair(oracle, emu_lib, n, k, rects, mode="red_black")
+    x, x0 = P.rnd(rng, n), P.rnd(rng, n)
+    dev.upload("velocities_x", x)
+    dev.upload("velocities_x0", x0)
+    dev.op_lin_solve(orient, "velocities_x", "velocities_x0", 0.37, 2.48, k)
+    oracle.lin_solve(orient, x, x0, 0.37, 2.48, k, ref.cells, red_black=True)
+    got = dev.download("velocities_x")
+    assert P.bits_equal(got, x), P.describe_diff(got, x)
+
+
 @pytest.mark.parametrize("kernel", ["slide", "stream"])
 @pytest.mark.parametrize("orient", [P.ROW, P.COL, P.PASSIVE])
 def test_red_black_sliding_window_kernels(oracle, emu_lib, orient, kernel, monkeypatch):
