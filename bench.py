@@ -252,6 +252,7 @@ KERNELS = {
     "red_black": "k_rb_stream (red-black Gauss-Seidel, one warp per 104-column strip sliding down the rows, rows brought in by "
                  "bulk copies, 4 iterations per launch)",
     "red_black_small": "k_rb_reg (red-black Gauss-Seidel, tile in registers, 4 iterations per launch)",
+    "red_black_one_cta": "k_rb_small (red-black Gauss-Seidel, whole grid in one SM's shared memory, all K iterations per launch)",
 }
 PHASES = ["lin_solve_ms", "advect_ms", "project_ms", "boundary_ms", "other_ms"]
 
@@ -305,7 +306,11 @@ def measure_mode(wl, wl_key, mode, steps, warmup, local_rank, rank, world, peak,
     ls_s = prof["lin_solve_ms"] * 1e-3
     if mode == "red_black":
         launches = max(1, solves * ((k + RB_ITERS_PER_LAUNCH - 1) // RB_ITERS_PER_LAUNCH))
-        kernel, tkey = KERNELS["red_black" if n >= RB_STREAM_MIN_N else "red_black_small"], "rb_dram_bytes_per_launch"
+        one_cta = world == 1 and n * ((n + 31) // 32 * 32) <= 32768               # eq_api.cu RBSM_MAX_CELLS
+        if one_cta:
+            launches = max(1, solves)
+        kernel = KERNELS["red_black" if n >= RB_STREAM_MIN_N else ("red_black_one_cta" if one_cta else "red_black_small")]
+        tkey = "rb_dram_bytes_per_launch"
     else:
         launches = max(1, solves)
         kernel, tkey = (KERNELS["exact"] if world == 1 else KERNELS["exact_slabs"]), "dram_bytes_per_launch"

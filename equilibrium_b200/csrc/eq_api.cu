@@ -861,7 +861,11 @@ static int lin_solve_red_black_slide(eq_fluid *h, const LinSolveReq *req, int nr
 // Streaming red-black kernel (k_rb_stream): RQ_T iterations per pass, rows brought in by bulk copies; what is left of
 // `iters` after the last full pass goes through k_rb_slide (2 or 1 iterations per pass).
 static int lin_solve_red_black_stream(eq_fluid *h, const LinSolveReq *req, int nreq, int64_t iters) {
-    const EqLayout L = h->L;
+    EqLayout L = h->L;
+#ifdef EQ_DEBUG_KNOBS
+    // timing experiments only (wrong results): pretend the slab has this many rows, to study small slabs on one GPU
+    if (debug_knob("EQ_RQ_DEBUG_ROWS")) L.row1 = std::min(L.row1, L.row0 + std::max(64, atoi(getenv("EQ_RQ_DEBUG_ROWS"))));
+#endif
     const int rows = L.row1 - L.row0;
     // k_rb_stream: a task (one warp) = a strip of RQ_SW columns x a segment of rows.  Every segment recomputes
     // 2 RQ_VH rows and fills its window (13 rows), so long segments waste less -- but the tasks differ in cost (rows with
