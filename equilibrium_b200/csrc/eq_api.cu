@@ -879,12 +879,26 @@ static int lin_solve_red_black_stream(eq_fluid *h, const LinSolveReq *req, int n
     for (int sx = nstrips - 1; sx >= 1 && sx * RQ_SW - RQ_HALO + 127 > L.N - 2; --sx) ++n_edge;
     n_edge = std::min(n_edge, nstrips);
     const int ns = nstrips - n_edge;
-    auto edge_rows = [&](int sr) { return std::min(rows, std::max(64, sr / 4)); };
+    const int slots = h->sm_count * RQ_CTAS_PER_SM;
     int nsegs = std::max(1, (rows + RQ_SEG_ROWS / 2) / RQ_SEG_ROWS);
-    nsegs = env_int("EQ_RQ_SEGS", nsegs);
+    // about one wave of tasks or less (a row slab, a mid-size grid): shorter tasks, down to 96 rows, as long as they stay
+    // within one and a half waves (2048-row slab of 16384 columns: 7 / 11 / 14 / 21 segments -> 0.80 / 0.65 / 0.63 / 0.57 ms)
+    if ((long long)std::max(1, ns) * nsegs <= (3LL * slots) / 2)
+        nsegs = std::max(nsegs, std::min(rows / 96, (int)((3LL * slots) / 2 / std::max(1, ns))));
+    nsegs = env_int("EQ_RQ_SEGS", std::max(1, nsegs));
     const int seg_rows = (rows + nsegs - 1) / nsegs;
     nsegs = (rows + seg_rows - 1) / seg_rows;
-    const int seg_rows_e = edge_rows(seg_rows), nsegs_e = (rows + seg_rows_e - 1) / seg_rows_e;
+    // Wall strips: a range-tested tick with set_boundaries on every row costs ~3.4 fast ticks.  With several waves of
+    // tasks they overlap with the rest (a quarter of the segment, at least 64 rows: less recomputation).  When the whole
+    // launch is about one wave -- a row slab of a multi-GPU run, a mid-size grid -- the launch lasts as long as its slowest
+    // task, so a wall task gets as many rows as make it last as long as an interior task (warm-up rows included), at least 16
+    // (measured on a 2048-row slab of 16384 columns: the launch took 0.17 ms whatever the interior segmentation was --
+    // the time of a 64 + 37 row wall task).
+    int seg_rows_e = std::max(64, seg_rows / 4);
+    if ((long long)ns * nsegs <= (3LL * slots) / 2)
+        seg_rows_e = std::max(16, (int)((seg_rows + 2 * RQ_VH + 13) * 0.3f) - (2 * RQ_VH + 13));
+    seg_rows_e = env_int("EQ_RQ_EDGE_ROWS", std::min(rows, seg_rows_e));
+    const int nsegs_e = (rows + seg_rows_e - 1) / seg_rows_e;
     const int grid = n_edge * nsegs_e + ns * nsegs;
     // k_rb_slide for the remainder
     const int nstrips2 = (L.N + RS_SW - 1) / RS_SW;
