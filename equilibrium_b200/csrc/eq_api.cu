@@ -911,12 +911,25 @@ static int lin_solve_red_black_stream(eq_fluid *h, const LinSolveReq *req, int n
         float *cur = req[i].x, *other = h->rb_tmp;
         TRY(halo_xchg(h, const_cast<float *>(req[i].x0), RB_H));    // the first / last segment recomputes ghost rows
         int64_t done = 0;
+        bool pushed = false;     // the previous k_rb_stream launch wrote my boundary rows into the neighbours' ghost rows
         while (done < iters) {
-            TRY(halo_xchg(h, cur, RB_H));                           // ghost rows of the current iterate (also the neighbour barrier)
+            // ghost rows of `cur`: copied by the exchange kernel, or already pushed by the pass that produced `cur`
+            // (then the exchange is only the neighbour barrier: nrows = 0)
+            TRY(halo_xchg(h, cur, pushed ? 0 : RB_H));
             if (iters - done >= RQ_T) {
-                EQ_LAUNCH(k_rb_stream, grid, RQ_THREADS, RQ_SMEM_BYTES, h->stream, cur, other, req[i].x0, h->codes, h->chunk_flags,
-                          req[i].a, c_recip, req[i].orient, L.row0, L.row1, nstrips, n_edge, nsegs, seg_rows, nsegs_e, seg_rows_e,
-                          h->run_if, L);
+                if (h->world > 1) {
+                    float *pu = nullptr, *pd = nullptr;
+                    TRY(peer_buffer(h, other, h->rank - 1, &pu));
+                    TRY(peer_buffer(h, other, h->rank + 1, &pd));
+                    EQ_LAUNCH(k_rb_stream<true>, grid, RQ_THREADS, RQ_SMEM_BYTES, h->stream, cur, other, req[i].x0, h->codes,
+                              h->chunk_flags, req[i].a, c_recip, req[i].orient, L.row0, L.row1, nstrips, n_edge, nsegs, seg_rows,
+                              nsegs_e, seg_rows_e, pu, pd, h->run_if, L);
+                    pushed = true;
+                } else {
+                    EQ_LAUNCH(k_rb_stream<false>, grid, RQ_THREADS, RQ_SMEM_BYTES, h->stream, cur, other, req[i].x0, h->codes,
+                              h->chunk_flags, req[i].a, c_recip, req[i].orient, L.row0, L.row1, nstrips, n_edge, nsegs, seg_rows,
+                              nsegs_e, seg_rows_e, nullptr, nullptr, h->run_if, L);
+                }
                 TRY(check_launch("k_rb_stream"));
                 done += RQ_T;
             } else {
@@ -924,6 +937,7 @@ static int lin_solve_red_black_stream(eq_fluid *h, const LinSolveReq *req, int n
                 EQ_LAUNCH(k_rb_slide, grid2, RS_THREADS, 0, h->stream, cur, other, req[i].x0, h->codes, h->chunk_flags, req[i].a,
                           c_recip, req[i].orient, it, L.row0, L.row1, nstrips2, nsegs2, seg_rows2, h->run_if, L);
                 TRY(check_launch("k_rb_slide"));
+                pushed = false;
                 done += it;
             }
             std::swap(cur, other);
@@ -1324,7 +1338,8 @@ static int alloc_handle(const EqParams *params, eq_fluid **out) {
     CU(cudaFuncSetAttribute(k_linsolve_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LSX_SMEM_BYTES));
     CU(cudaFuncSetAttribute(k_rb_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RB_SMEM_BYTES));
     CU(cudaFuncSetAttribute(k_rb_reg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RBR_SMEM_BYTES));
-    CU(cudaFuncSetAttribute(k_rb_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RQ_SMEM_BYTES));
+    CU(cudaFuncSetAttribute(k_rb_stream<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RQ_SMEM_BYTES));
+    CU(cudaFuncSetAttribute(k_rb_stream<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RQ_SMEM_BYTES));
     CU(cudaFuncSetAttribute(k_rb_small<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(RBSM_MAX_CELLS * sizeof(float))));
     CU(cudaFuncSetAttribute(k_rb_small<RBSM_MAXR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(RBSM_MAX_CELLS * sizeof(float))));
     int per_sm = 0;

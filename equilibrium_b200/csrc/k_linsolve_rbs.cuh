@@ -264,6 +264,8 @@ struct RqTask {
     const float *__restrict__ x0;
     const uint8_t *__restrict__ codes;
     float *__restrict__ xout;
+    float *push_up, *push_dn;                                        // the neighbours' copies of xout (row slabs), or nullptr
+    int push_lo, push_hi;                                            // rows < push_lo go up as well, rows >= push_hi down
     unsigned char *wsm;
     float a, c_recip;
     int N, P, X0c, ys, ye, t_last, cb, qb;
@@ -445,7 +447,7 @@ struct RqTask {
         ooff = (unsigned)(tb - 3 * RQ_T + 1) * (unsigned)P + (unsigned)c0;
     }
     // ticks tb .. tb + 3 (tb a multiple of 4); true when the task is finished
-    template <bool GUARD, bool FIX, int ORIENT>
+    template <bool GUARD, bool FIX, int ORIENT, bool PUSH>
     __device__ __forceinline__ bool ticks4(int tb) {
         const bool st_lane = (lane >= RQ_HALO / 4 && lane < 32 - RQ_HALO / 4) && c0 < N;
 #pragma unroll
@@ -480,6 +482,12 @@ struct RqTask {
                     for (int e = 0; e < 4; ++e)
                         if (c0 + e < N) outp[e] = o[e];
                 }
+                if (PUSH) {
+                    // the first / last RQ_VH rows of the slab are the neighbours' ghost rows of the next pass: written
+                    // straight into their copy of the array over NVLink (whole quads: the pad columns are never read)
+                    float *peer = (yo < push_lo) ? push_up : ((yo >= push_hi) ? push_dn : nullptr);
+                    if (peer && st_lane) *reinterpret_cast<float4 *>(peer + ooff) = make_float4(o[0], o[1], o[2], o[3]);
+                }
             }
             // row tau + 5 replaces row tau - 11 (x0, codes) and row tau + 1 (x ring, taken in this tick; the shuffles
             // above have brought every lane past that read)
@@ -492,11 +500,11 @@ struct RqTask {
         ph ^= 1u;
         return false;
     }
-    template <bool GUARD, bool FIX, int ORIENT>
+    template <bool GUARD, bool FIX, int ORIENT, bool PUSH>
     __device__ __forceinline__ bool block(int tb) {
 #pragma unroll 1
         for (int q = 0; q < RQ_BLOCK / 4; ++q)
-            if (ticks4<GUARD, FIX, ORIENT>(tb + 4 * q)) return true;
+            if (ticks4<GUARD, FIX, ORIENT, PUSH>(tb + 4 * q)) return true;
         return false;
     }
 };
@@ -504,11 +512,15 @@ struct RqTask {
 // One task per CTA (= one warp).  The first n_edge * nsegs_e tasks are the strips that touch the left or right wall
 // (strip 0 and the last n_edge - 1: mirror codes on every row and range tests, the slow ones) in short segments -- they
 // go first --, the others the interior strips in segments of seg_rows.
+// PUSH (row slabs): the tasks that produce the slab's first / last RQ_VH rows also write them into push_up / push_dn, the
+// neighbours' copies of xout, so that only a barrier separates two passes.
+template <bool PUSH>
 __global__ void __launch_bounds__(RQ_THREADS, RQ_CTAS_PER_SM) k_rb_stream(const float *__restrict__ xin, float *__restrict__ xout,
                                                           const float *__restrict__ x0, const uint8_t *__restrict__ codes,
                                                           const uint8_t *__restrict__ chunk_flags, float a, float c_recip, int orient,
                                                           int row_lo, int row_hi, int nstrips, int n_edge, int nsegs, int seg_rows,
-                                                          int nsegs_e, int seg_rows_e, const unsigned *__restrict__ run_if, EqLayout L) {
+                                                          int nsegs_e, int seg_rows_e, float *push_up, float *push_dn,
+                                                          const unsigned *__restrict__ run_if, EqLayout L) {
     EQ_DYN_SMEM(rq_smem);
     if (run_if && *run_if == 0u) return;                                   // the a == 0 shortcut was taken (k_a0_check)
     const int lane = (int)threadIdx.x;
@@ -536,6 +548,8 @@ __global__ void __launch_bounds__(RQ_THREADS, RQ_CTAS_PER_SM) k_rb_stream(const 
     }
     const int N = L.N;
     T.xin = xin; T.xout = xout; T.x0 = x0; T.codes = codes;
+    T.push_up = push_up; T.push_dn = push_dn;
+    T.push_lo = row_lo + RQ_VH; T.push_hi = row_hi - RQ_VH;
     T.a = a; T.c_recip = c_recip;
     T.X0c = sx * RQ_SW - RQ_HALO;
     T.ys = ys; T.ye = ye; T.lane = lane;
@@ -575,14 +589,14 @@ __global__ void __launch_bounds__(RQ_THREADS, RQ_CTAS_PER_SM) k_rb_stream(const 
         if (use_flags) nf = block_flags(tb + RQ_BLOCK);                    // needed RQ_BLOCK ticks from now
         bool fin;
         if (guard) {
-            if (orient == EQ_ADJUST_ROW) fin = T.block<true, true, EQ_ADJUST_ROW>(tb);
-            else if (orient == EQ_ADJUST_COLUMN) fin = T.block<true, true, EQ_ADJUST_COLUMN>(tb);
-            else fin = T.block<true, true, EQ_PASSIVE>(tb);
+            if (orient == EQ_ADJUST_ROW) fin = T.block<true, true, EQ_ADJUST_ROW, PUSH>(tb);
+            else if (orient == EQ_ADJUST_COLUMN) fin = T.block<true, true, EQ_ADJUST_COLUMN, PUSH>(tb);
+            else fin = T.block<true, true, EQ_PASSIVE, PUSH>(tb);
         } else if (fix) {
-            if (orient == EQ_ADJUST_ROW) fin = T.block<false, true, EQ_ADJUST_ROW>(tb);
-            else fin = T.block<false, true, EQ_ADJUST_COLUMN>(tb);         // (Passive: no codes away from the frame)
+            if (orient == EQ_ADJUST_ROW) fin = T.block<false, true, EQ_ADJUST_ROW, PUSH>(tb);
+            else fin = T.block<false, true, EQ_ADJUST_COLUMN, PUSH>(tb);   // (Passive: no codes away from the frame)
         } else {
-            fin = T.block<false, false, EQ_PASSIVE>(tb);
+            fin = T.block<false, false, EQ_PASSIVE, PUSH>(tb);
         }
         if (fin) break;
     }
