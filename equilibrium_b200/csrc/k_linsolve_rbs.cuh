@@ -399,28 +399,41 @@ struct RqTask {
         constexpr unsigned SGN = (ORIENT != EQ_PASSIVE) ? 0x80000000u : 0u;
         // most rows of a strip carry no code at all: one vote instead of the selects
         if (!__any_sync(0xffffffffu, (cw & VM) != 0u)) return;
-        float lft = 0.f, rgt = 0.f;
+        // branch-free: a cell's code bits become all-ones / zero masks, the cell takes the OR of its masked candidates
+        // (ptxas compiled a chain of ?: into divergent branches with a reconvergence barrier per cell)
+        unsigned lft = 0u, rgt = 0u;
         if (ORIENT != EQ_ADJUST_COLUMN) {
-            lft = __shfl_up_sync(0xffffffffu, r[3], 1);
-            rgt = __shfl_down_sync(0xffffffffu, r[0], 1);
+            lft = __float_as_uint(__shfl_up_sync(0xffffffffu, r[3], 1));
+            rgt = __float_as_uint(__shfl_down_sync(0xffffffffu, r[0], 1));
         }
-        float nv[4];
+        const unsigned me[4] = {__float_as_uint(r[0]), __float_as_uint(r[1]), __float_as_uint(r[2]), __float_as_uint(r[3])};
+        unsigned nv[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            const unsigned d = rs_decode<ORIENT>((cw >> (8 * e)) & 255u);
-            float src = r[e];
-            if (ORIENT != EQ_ADJUST_COLUMN) {
-                src = (d == WF_C_L) ? (e == 0 ? lft : r[e > 0 ? e - 1 : 0]) : src;
-                src = (d == WF_C_R) ? (e == 3 ? rgt : r[e < 3 ? e + 1 : 3]) : src;
+            const unsigned b = cw >> (8 * e);
+            unsigned mL = 0u, mR = 0u, mU = 0u, mD = 0u;
+            if (ORIENT == EQ_ADJUST_ROW) {                            // bits 0-1: 1 = LEFT, 2 = RIGHT
+                mL = 0u - (b & 1u);
+                mR = 0u - ((b >> 1) & 1u);
+            } else if (ORIENT == EQ_ADJUST_COLUMN) {                  // bits 2-3: 1 = UP, 2 = DOWN
+                mU = 0u - ((b >> 2) & 1u);
+                mD = 0u - ((b >> 3) & 1u);
+            } else {                                                  // bits 4-6: WF_C_L .. WF_C_D
+                const unsigned d = (b >> EQ_CODE_PASSIVE_SHIFT) & 7u;
+                mL = 0u - (unsigned)(d == WF_C_L);
+                mR = 0u - (unsigned)(d == WF_C_R);
+                mU = 0u - (unsigned)(d == WF_C_U);
+                mD = 0u - (unsigned)(d == WF_C_D);
             }
-            if (ORIENT != EQ_ADJUST_ROW) {
-                src = (d == WF_C_U) ? up[e] : src;
-                src = (d == WF_C_D) ? dn[e] : src;
-            }
-            nv[e] = (d != WF_C_NONE) ? __uint_as_float(__float_as_uint(src) ^ SGN) : src;
+            const unsigned any = mL | mR | mU | mD;
+            const unsigned vl = (e == 0) ? lft : me[e > 0 ? e - 1 : 0], vr = (e == 3) ? rgt : me[e < 3 ? e + 1 : 3];
+            unsigned v = me[e] & ~any;
+            if (ORIENT != EQ_ADJUST_COLUMN) v |= (vl & mL) | (vr & mR);
+            if (ORIENT != EQ_ADJUST_ROW) v |= (__float_as_uint(up[e]) & mU) | (__float_as_uint(dn[e]) & mD);
+            nv[e] = v ^ (SGN & any);
         }
 #pragma unroll
-        for (int e = 0; e < 4; ++e) r[e] = nv[e];
+        for (int e = 0; e < 4; ++e) r[e] = __uint_as_float(nv[e]);
     }
     __device__ __forceinline__ void next_row() {
         ooff += (unsigned)P;
