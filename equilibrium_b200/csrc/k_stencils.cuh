@@ -385,9 +385,16 @@ __device__ __forceinline__ AdvSample eq_backtrace(float fi, float fj, float u, f
 // The back-trace may leave the slab: each sample row is read from the rank that owns it (direct
 // peer loads over NVLink; one rank => the local array).
 template <bool PEERS>
-__device__ __forceinline__ float eq_bilinear(const AdvSample &r, const EqPeerTable &t, int P) {
-    // one rank: no owner look-up (it would index the parameter table dynamically and block the hoisting of the gathers)
-    const float *lo = PEERS ? eq_owner_base(t, r.j0) : t.base[0], *hi = PEERS ? eq_owner_base(t, r.j1) : t.base[0];
+__device__ __forceinline__ float eq_bilinear(const AdvSample &r, const EqPeerTable &t, int P, const float *mine, unsigned row0,
+                                             unsigned row1) {
+    // one rank: no owner look-up (it would index the parameter table dynamically and block the hoisting of the gathers).
+    // Row slabs: almost every back-trace stays inside the rows this rank owns -- those lanes read the local array and
+    // only the others search the table (a warp without such a lane skips the branch)
+    const float *lo = mine, *hi = mine;
+    if (PEERS && !(r.j0 >= row0 && r.j1 < row1)) {
+        lo = eq_owner_base(t, r.j0);
+        hi = eq_owner_base(t, r.j1);
+    }
     const float a = lo[r.o00], b = hi[r.o01];
     const float c = lo[r.o10], d = hi[r.o11];
     const float l = __fadd_rn(__fmul_rn(r.t0, a), __fmul_rn(r.t1, b));
@@ -402,6 +409,7 @@ __global__ void __launch_bounds__(EQ_ADV_THREADS) k_advect(float *__restrict__ d
                                                            float dt, EqLayout L) {
     const int N = L.N, P = L.P;
     const int j = blockIdx.x + max(L.row0, 1);              // owned interior rows
+    const float *mineA = PEERS ? d0A.base[L.rank] : d0A.base[0], *mineB = PEERS ? d0B.base[L.rank] : d0B.base[0];
     const float nf = (float)N;
     const float dtx = __fmul_rn(dt, (float)(N - 2));                   // :390
     const float fj = (float)j;
@@ -446,8 +454,8 @@ __global__ void __launch_bounds__(EQ_ADV_THREADS) k_advect(float *__restrict__ d
             float a[EQ_ADV_U], b[EQ_ADV_U];
 #pragma unroll
             for (int q = 0; q < EQ_ADV_U; ++q) {
-                a[q] = eq_bilinear<PEERS>(r[q], d0A, P);
-                b[q] = (NF == 2) ? eq_bilinear<PEERS>(r[q], d0B, P) : 0.f;
+                a[q] = eq_bilinear<PEERS>(r[q], d0A, P, mineA, (unsigned)L.row0, (unsigned)L.row1);
+                b[q] = (NF == 2) ? eq_bilinear<PEERS>(r[q], d0B, P, mineB, (unsigned)L.row0, (unsigned)L.row1) : 0.f;
             }
 #pragma unroll
             for (int q = 0; q < EQ_ADV_U; ++q) {
@@ -468,15 +476,15 @@ __global__ void __launch_bounds__(EQ_ADV_THREADS) k_advect(float *__restrict__ d
             if (i > last) continue;
             float a, b = 0.f;
             if (i < f) {
-                a = eq_bilinear<PEERS>(r[q], d0A, P);
-                if (NF == 2) b = eq_bilinear<PEERS>(r[q], d0B, P);
+                a = eq_bilinear<PEERS>(r[q], d0A, P, mineA, (unsigned)L.row0, (unsigned)L.row1);
+                if (NF == 2) b = eq_bilinear<PEERS>(r[q], d0B, P, mineB, (unsigned)L.row0, (unsigned)L.row1);
             } else if (i == 1) {                                       // :421, f == 1: the frame cell, untouched
                 a = dA[row];
                 if (NF == 2) b = dB[row];
             } else {                                                   // :421 copy of the updated left cell
                 const AdvSample rl = eq_backtrace((float)(i - 1), fj, vx[row + i - 1], vy[row + i - 1], dtx, nf, N, P);
-                a = eq_bilinear<PEERS>(rl, d0A, P);
-                if (NF == 2) b = eq_bilinear<PEERS>(rl, d0B, P);
+                a = eq_bilinear<PEERS>(rl, d0A, P, mineA, (unsigned)L.row0, (unsigned)L.row1);
+                if (NF == 2) b = eq_bilinear<PEERS>(rl, d0B, P, mineB, (unsigned)L.row0, (unsigned)L.row1);
             }
             dA[row + i] = a;
             if (NF == 2) dB[row + i] = b;
