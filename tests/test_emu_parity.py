@@ -212,6 +212,22 @@ def test_red_black_sliding_window_kernels(oracle, emu_lib, orient, kernel, monke
     assert P.bits_equal(got, x), P.describe_diff(got, x)
 
 
+def test_red_black_default_kernel_choice_at_2048(oracle, emu_lib):
+    # no EQ_RB_KERNEL: a 2048-column grid takes k_rb_stream by default, with the task shapes the library picks for a
+    # launch of less than one wave (96-row segments, wall-strip tasks sized to match); 5 iterations = one pass of 4 through
+    # k_rb_stream and one of 1 through k_rb_slide.  ~20 s under the emulator.
+    rng = np.random.default_rng(1)
+    n, k = 2048, 5
+    dev, ref = P.make_pair(oracle, emu_lib, n, k, [(300, 40, 330, 900), (1000, 1200, 1900, 1230)], mode="red_black")
+    x, x0 = P.rnd(rng, n), P.rnd(rng, n)
+    dev.upload("velocities_x", x)
+    dev.upload("velocities_x0", x0)
+    dev.op_lin_solve(P.ROW, "velocities_x", "velocities_x0", 0.37, 2.48, k)
+    oracle.lin_solve(P.ROW, x, x0, 0.37, 2.48, k, ref.cells, red_black=True)
+    got = dev.download("velocities_x")
+    assert P.bits_equal(got, x), P.describe_diff(got, x)
+
+
 @pytest.mark.parametrize("n,steps", [(64, 1), (101, 0)])      # (the GPU suite runs more frames; emulated steps are slow)
 def test_render_rgba_and_snapshots(oracle, emu_lib, n, steps):
     P.check_render_and_snapshot(oracle, emu_lib, n, [(10, 10, 20, 30), (40, 5, 50, 60)], steps=steps)
